@@ -1,0 +1,177 @@
+/* include/kd_capi.h
+ *
+ * C ABI of the B200-native token-passing Viterbi beam search.
+ *
+ * This is the drop-in boundary for the reference's FasterDecoder hot path
+ * (k2-fsa/kaldi-decoder, kaldi-decoder/csrc/faster-decoder.{h,cc}): plain
+ * pointers and sizes, no C++ or torch types.  The C++ classes in
+ * kaldi-decoder_b200/csrc/ (same names and signatures as the reference's) and
+ * the Python bindings are thin layers over exactly these entry points.
+ * Every function returns KD_OK (0) or a negative status; kd_last_error() gives
+ * the message for the calling thread (the reference signals errors by
+ * throwing std::runtime_error from KALDI_DECODER_ERR / KALDI_DECODER_ASSERT,
+ * log.h:46-51,86-89 -- the C++ wrapper rethrows from these statuses).
+ *
+ * There is NO CPU fallback: every call needs a CUDA device (sm_100a build).
+ *
+ * Execution model.  A kd_decoder owns `max_lanes` independent utterance lanes
+ * (one reference FasterDecoder object == one lane).  All per-lane search
+ * state (tokens, recombination table, backpointer store) stays resident in
+ * device memory between calls, so InitDecoding / AdvanceDecoding streaming
+ * works across calls exactly as in the reference (faster-decoder.cc:126-152).
+ */
+#ifndef KD_CAPI_H_
+#define KD_CAPI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define KD_API __declspec(dllexport)
+#else
+#define KD_API __attribute__((visibility("default")))
+#endif
+
+enum {
+  KD_OK = 0,
+  KD_ERR_INVALID = -1,   /* bad argument / failed reference-style assertion   */
+  KD_ERR_CUDA = -2,      /* CUDA runtime error                                */
+  KD_ERR_OVERFLOW = -3,  /* a per-lane device capacity was exceeded           */
+  KD_ERR_NO_DEVICE = -4  /* no usable CUDA device                             */
+};
+
+enum { KD_MEM_HOST = 0, KD_MEM_DEVICE = 1 };
+
+typedef struct kd_graph kd_graph;
+typedef struct kd_decoder kd_decoder;
+
+/* FasterDecoderOptions (faster-decoder.h:24-63).  hash_ratio is accepted for
+ * signature compatibility and only validated (>= 1.0, faster-decoder.cc:24). */
+typedef struct kd_options {
+  float beam;
+  int32_t max_active;
+  int32_t min_active;
+  float beam_delta;
+  float hash_ratio;
+} kd_options;
+
+/* Device capacities; any field <= 0 picks a default. */
+typedef struct kd_decoder_config {
+  int32_t max_lanes;        /* number of utterance lanes (default 1)                   */
+  int32_t hash_capacity;    /* per-lane recombination-table entries, power of two;
+                               tokens alive in one frame must stay <= capacity / 2     */
+  int64_t arena_records;    /* per-lane backpointer-store records (sum over frames of
+                               tokens alive at frame end), 20 bytes each               */
+  int32_t threads_per_lane; /* 128/256/512/1024; default chosen from max_lanes         */
+  int32_t lanes_per_group;  /* host-memory advance: lanes per copy/compute stage       */
+} kd_decoder_config;
+
+/* Search counters, summed over the frames decoded since kd_decoder_init.  They
+ * define the algorithmic bytes of SURVEY.md §8(d):
+ *   16*(emit_arcs + eps_arcs) + 16*tokens_in + 24*tokens_out + 4*cols*frames */
+typedef struct kd_stats {
+  int64_t frames;
+  int64_t tokens_in;       /* tokens at frame start                               */
+  int64_t tokens_expanded; /* tokens with cost < weight_cutoff                    */
+  int64_t emit_arcs;       /* emitting arcs visited                               */
+  int64_t eps_arcs;        /* epsilon arcs visited in the closure                 */
+  int64_t tokens_out;      /* tokens alive at frame end                           */
+  int64_t max_tokens;      /* max tokens alive at a frame end                     */
+  int64_t eps_sweeps;      /* closure sweeps                                      */
+} kd_stats;
+
+KD_API const char *kd_last_error(void);
+
+/* Number of CUDA devices visible (0 when there is none). */
+KD_API int kd_device_count(int *count);
+
+/* ---- graph: replaces the `const fst::Fst<fst::StdArc>&` the reference binds
+ * (faster-decoder.cc:21-23, faster-decoder.h:179).  Input is the FST as CSR in
+ * its original arc order: arcs of state s are [row_offsets[s], row_offsets[s+1]).
+ * final_weight[s] = +inf for non-final states (TropicalWeight::Zero()).
+ * The graph is copied to `device` as a split (emitting / epsilon) 16-byte-arc
+ * CSR; it is immutable and may be shared by any number of decoders. */
+KD_API int kd_graph_create(int device, int32_t num_states, int32_t start,
+                           const int64_t *row_offsets, const int32_t *ilabel,
+                           const int32_t *olabel, const float *weight,
+                           const int32_t *nextstate, const float *final_weight,
+                           kd_graph **out);
+KD_API int kd_graph_destroy(kd_graph *g);
+/* info[0..4] = num_states, num_arcs, num_epsilon_arcs, max_ilabel, device */
+KD_API int kd_graph_info(const kd_graph *g, int64_t info[5]);
+
+/* ---- decoder: FasterDecoder::FasterDecoder (faster-decoder.cc:21-32); the
+ * option checks of lines 24-28 are enforced here and in kd_decoder_set_options. */
+KD_API int kd_decoder_create(kd_graph *g, const kd_options *opts,
+                             const kd_decoder_config *cfg, kd_decoder **out);
+KD_API int kd_decoder_destroy(kd_decoder *d);
+/* FasterDecoder::SetOptions (faster-decoder.h:78) */
+KD_API int kd_decoder_set_options(kd_decoder *d, const kd_options *opts);
+
+/* FasterDecoder::InitDecoding (faster-decoder.cc:42-56) for n lanes. */
+KD_API int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes);
+
+/* FasterDecoder::AdvanceDecoding (faster-decoder.cc:126-152) with a
+ * DecodableCtc per lane (decodable-ctc.cc:22-31): lane lanes[i] sees the
+ * row-major float matrix logprobs[i] of rows[i] x cols whose first row is frame
+ * offsets[i] (offsets may be NULL = all 0); NumFramesReady = offsets[i] + rows[i].
+ * max_num_frames < 0 means "all ready frames".  mem_kind says where the
+ * matrices live; host matrices are copied (pinned memory makes the copy
+ * asynchronous and overlapped with the search).  Returns when all lanes have
+ * advanced. */
+KD_API int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
+                              const float *const *logprobs, const int32_t *rows,
+                              int32_t cols, const int32_t *offsets,
+                              int32_t max_num_frames, int mem_kind);
+
+/* FasterDecoder::NumFramesDecoded (faster-decoder.h:107); -1 before init. */
+KD_API int kd_decoder_num_frames_decoded(kd_decoder *d, int32_t lane, int32_t *out);
+
+/* FasterDecoder::ReachedFinal (faster-decoder.cc:347-354). */
+KD_API int kd_decoder_reached_final(kd_decoder *d, int32_t lane, int32_t *out);
+
+/* FasterDecoder::GetBestPath (faster-decoder.cc:356-424) up to, and not
+ * including, RemoveEpsLocal: one (ilabel, olabel, graph cost, acoustic cost)
+ * arc per token on the best path, in time order; final_weight = (graph,
+ * acoustic) of the final state as the reference sets it at lines 416-421.
+ * Step 1 selects the best token of each lane and measures its path; step 2
+ * writes lane lanes[i]'s arcs at out_offsets[i].. of the host arrays. */
+KD_API int kd_decoder_best_path_prepare(kd_decoder *d, int32_t n, const int32_t *lanes,
+                                        int use_final_probs, int32_t *ok,
+                                        int32_t *reached_final, int64_t *num_arcs);
+KD_API int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
+                                      const int64_t *out_offsets, int64_t total_arcs,
+                                      int32_t *ilabel, int32_t *olabel, float *graph_cost,
+                                      float *acoustic_cost, float *final_weight2);
+/* Single-lane convenience: both steps; *num_arcs is the path length even if it
+ * exceeds cap (then nothing is written and KD_ERR_INVALID is returned). */
+KD_API int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs, int64_t cap,
+                                int32_t *ilabel, int32_t *olabel, float *graph_cost,
+                                float *acoustic_cost, int64_t *num_arcs,
+                                float final_weight2[2], int32_t *reached_final, int32_t *ok);
+
+/* The live tokens of a lane (state, cost), in device order (unordered): the
+ * contents of the reference's `toks_` list.  *n is the token count even if it
+ * exceeds cap. */
+KD_API int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *states,
+                                  double *costs, int64_t *n);
+
+/* Counters of one lane, or summed over all lanes when lane < 0. */
+KD_API int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out);
+
+/* Device time (ms, CUDA events on the decoder's streams) of the search kernels
+ * of the last kd_decoder_advance call, and how many kernels it launched. */
+KD_API int kd_decoder_last_advance_info(kd_decoder *d, float *kernel_ms, int32_t *launches);
+
+/* info[0..5] = max_lanes, hash_capacity, arena_records, threads_per_lane,
+ *              device bytes allocated, lanes_per_group */
+KD_API int kd_decoder_info(kd_decoder *d, int64_t info[6]);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* KD_CAPI_H_ */

@@ -1,0 +1,866 @@
+// kaldi-decoder_b200/csrc/kd_capi.cu
+//
+// Host side of the C ABI declared in include/kd_capi.h: graph ingest (the
+// reference's `const fst::Fst<StdArc>&`, faster-decoder.cc:21-23, becomes a
+// device-resident split CSR), lane/arena/table allocation, kernel launches,
+// host<->device staging.  No CPU implementation of the search lives here: if
+// there is no CUDA device every entry point fails.
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kd_capi.h"
+#include "kd_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_error;
+
+int Fail(int code, const std::string &msg) {
+  g_error = msg;
+  return code;
+}
+
+#define KD_CUDA(expr)                                                              \
+  do {                                                                             \
+    cudaError_t kd_e_ = (expr);                                                    \
+    if (kd_e_ != cudaSuccess) {                                                    \
+      return Fail(KD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(kd_e_)); \
+    }                                                                              \
+  } while (0)
+
+constexpr int kNumStreams = 8;
+constexpr int kNumSMsFallback = 148;
+
+template <class T>
+int DevAlloc(T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  KD_CUDA(cudaMalloc(reinterpret_cast<void **>(p), n * sizeof(T)));
+  return KD_OK;
+}
+
+}  // namespace
+
+struct kd_graph {
+  int device = 0;
+  int64_t num_states = 0, num_arcs = 0, num_emit = 0, num_eps = 0;
+  int32_t start = -1, max_ilabel = 0;
+  int4 *st = nullptr;
+  int4 *e_arc = nullptr;
+  int4 *n_arc = nullptr;
+  float *fin = nullptr;
+};
+
+struct kd_decoder {
+  kd_graph *g = nullptr;
+  kd_options opts;
+  int device = 0;
+  int num_sms = kNumSMsFallback;
+  int32_t max_lanes = 1;
+  uint32_t hcap = 0, lcap = 0, qcap = 0;
+  int64_t arena_cap = 0;
+  int32_t threads = 0;  // 0 = auto per launch
+  int32_t lanes_per_group = 128;
+  size_t device_bytes = 0;
+
+  kd::LaneState *lanes = nullptr;
+  double *a_cost = nullptr;
+  unsigned long long *a_link = nullptr;
+  int32_t *a_state = nullptr;
+  int32_t *hkey = nullptr;
+  kd::HVal *hval = nullptr;
+  uint32_t *hidx = nullptr;
+  uint32_t *list = nullptr;
+  uint32_t *queue = nullptr;
+  kd::AdvanceItem *d_items = nullptr;
+  int32_t *d_counters = nullptr;  // one per launch slot
+  int32_t n_counters = 0;
+  long long *d_out_off = nullptr;
+
+  // growable device scratch
+  float *d_stage = nullptr;
+  size_t stage_floats = 0;
+  int32_t *d_il = nullptr, *d_ol = nullptr;
+  float *d_gw = nullptr, *d_aw = nullptr;
+  int64_t path_cap = 0;
+
+  // pinned host mirrors
+  kd::AdvanceItem *h_items = nullptr;
+  kd::LaneState *h_lanes = nullptr;
+  long long *h_out_off = nullptr;
+
+  std::vector<int32_t> frames;  // host mirror of num_frames_decoded_, -1 = not initialised
+  std::vector<int32_t> status;
+  int last_use_final = 1;
+
+  cudaStream_t streams[kNumStreams] = {};
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+  cudaEvent_t ev_stream[kNumStreams] = {};
+  float last_kernel_ms = 0.f;
+  int32_t last_launches = 0;
+};
+
+namespace {
+
+int CheckOptions(const kd_options *o) {
+  // faster-decoder.cc:24-28
+  if (!o) return Fail(KD_ERR_INVALID, "options is null");
+  if (!(o->hash_ratio >= 1.0f))
+    return Fail(KD_ERR_INVALID, "Check failed!\nx: config_.hash_ratio >= 1.0");
+  if (!(o->max_active > 1))
+    return Fail(KD_ERR_INVALID, "Check failed!\nx: config_.max_active > 1");
+  if (!(o->min_active >= 0 && o->min_active < o->max_active))
+    return Fail(KD_ERR_INVALID,
+                "Check failed!\nx: config_.min_active >= 0 && config_.min_active < "
+                "config_.max_active");
+  return KD_OK;
+}
+
+kd::Params MakeParams(const kd_decoder *d) {
+  kd::Params P;
+  memset(&P, 0, sizeof(P));
+  P.st = d->g->st;
+  P.e_arc = d->g->e_arc;
+  P.n_arc = d->g->n_arc;
+  P.fin = d->g->fin;
+  P.start = d->g->start;
+  P.beam = d->opts.beam;
+  P.max_active = d->opts.max_active;
+  P.min_active = d->opts.min_active;
+  P.beam_delta = d->opts.beam_delta;
+  P.lanes = d->lanes;
+  P.items = d->d_items;
+  P.a_cost = d->a_cost;
+  P.a_link = d->a_link;
+  P.a_state = d->a_state;
+  P.arena_cap = d->arena_cap;
+  P.hkey = d->hkey;
+  P.hval = d->hval;
+  P.hidx = d->hidx;
+  P.list = d->list;
+  P.queue = d->queue;
+  P.hcap = d->hcap;
+  P.hmask = d->hcap - 1;
+  P.lcap = d->lcap;
+  P.qcap = d->qcap;
+  int lg = 0;
+  while ((1u << lg) < d->hcap) ++lg;
+  P.hshift = 32 - lg;
+  return P;
+}
+
+int PickThreads(const kd_decoder *d, int n_items) {
+  if (d->threads > 0) return d->threads;
+  if (n_items >= 4 * d->num_sms) return 128;
+  if (n_items >= 2 * d->num_sms) return 256;
+  return 512;
+}
+
+template <int THREADS>
+int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
+  size_t smem = (THREADS / 32) * 32 * (sizeof(double) + 2 * sizeof(uint32_t));
+  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(float);
+  int per_sm = 1;
+  KD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+      &per_sm, kd::kd_advance_kernel<THREADS>, THREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  int grid = std::min(n_items, per_sm * d->num_sms);
+  kd::kd_advance_kernel<THREADS><<<grid, THREADS, smem, s>>>(P);
+  KD_CUDA(cudaGetLastError());
+  d->last_launches++;
+  return KD_OK;
+}
+
+int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
+                  cudaStream_t s) {
+  switch (threads) {
+    case 128:
+      return LaunchAdvanceT<128>(d, P, n_items, s);
+    case 256:
+      return LaunchAdvanceT<256>(d, P, n_items, s);
+    case 512:
+      return LaunchAdvanceT<512>(d, P, n_items, s);
+    default:
+      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 256 or 512");
+  }
+}
+
+const char *StatusText(int st) {
+  if (st & kd::kStatusHashOverflow)
+    return "recombination table overflow (raise kd_decoder_config.hash_capacity)";
+  if (st & kd::kStatusArenaOverflow)
+    return "backpointer arena overflow (raise kd_decoder_config.arena_records)";
+  if (st & kd::kStatusQueueOverflow)
+    return "epsilon worklist overflow (raise kd_decoder_config.hash_capacity)";
+  return "unknown device status";
+}
+
+int CheckLanes(const kd_decoder *d, int32_t n, const int32_t *lanes) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  if (n < 0 || (n > 0 && !lanes)) return Fail(KD_ERR_INVALID, "bad lane list");
+  if (n > d->max_lanes) return Fail(KD_ERR_INVALID, "more lanes than max_lanes");
+  for (int32_t i = 0; i < n; ++i)
+    if (lanes[i] < 0 || lanes[i] >= d->max_lanes)
+      return Fail(KD_ERR_INVALID, "lane id out of range");
+  return KD_OK;
+}
+
+// Pulls the device lane states of `lanes` into the pinned mirror.
+int FetchLaneStates(kd_decoder *d, int32_t n, const int32_t *lanes) {
+  if (n == 0) return KD_OK;
+  int32_t lo = lanes[0], hi = lanes[0];
+  for (int32_t i = 1; i < n; ++i) {
+    lo = std::min(lo, lanes[i]);
+    hi = std::max(hi, lanes[i]);
+  }
+  KD_CUDA(cudaMemcpyAsync(d->h_lanes + lo, d->lanes + lo,
+                          sizeof(kd::LaneState) * static_cast<size_t>(hi - lo + 1),
+                          cudaMemcpyDeviceToHost, d->streams[0]));
+  KD_CUDA(cudaStreamSynchronize(d->streams[0]));
+  return KD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *kd_last_error(void) { return g_error.c_str(); }
+
+int kd_device_count(int *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  if (count) *count = n;
+  return KD_OK;
+}
+
+int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t *row_offsets,
+                    const int32_t *ilabel, const int32_t *olabel, const float *weight,
+                    const int32_t *nextstate, const float *final_weight, kd_graph **out) {
+  if (!out) return Fail(KD_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (num_states <= 0 || !row_offsets || !final_weight)
+    return Fail(KD_ERR_INVALID, "empty graph");
+  // faster-decoder.cc:47: InitDecoding asserts Start() != kNoStateId
+  if (start < 0 || start >= num_states)
+    return Fail(KD_ERR_INVALID, "Check failed!\nx: start_state != fst::kNoStateId");
+  const int64_t E = row_offsets[num_states];
+  if (row_offsets[0] != 0 || E < 0) return Fail(KD_ERR_INVALID, "bad row_offsets");
+  if (E > 0 && (!ilabel || !olabel || !weight || !nextstate))
+    return Fail(KD_ERR_INVALID, "null arc arrays");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return Fail(KD_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return Fail(KD_ERR_INVALID, "device index out of range");
+  KD_CUDA(cudaSetDevice(device));
+
+  std::vector<int4> st(num_states);
+  int64_t n_emit = 0, n_eps = 0;
+  int32_t max_il = 0;
+  for (int32_t s = 0; s < num_states; ++s) {
+    if (row_offsets[s + 1] < row_offsets[s]) return Fail(KD_ERR_INVALID, "bad row_offsets");
+    int64_t ne = 0, nn = 0;
+    for (int64_t a = row_offsets[s]; a < row_offsets[s + 1]; ++a) {
+      if (ilabel[a] < 0) return Fail(KD_ERR_INVALID, "negative ilabel");
+      if (nextstate[a] < 0 || nextstate[a] >= num_states)
+        return Fail(KD_ERR_INVALID, "arc nextstate out of range");
+      if (ilabel[a] != 0) {
+        ++ne;
+        max_il = std::max(max_il, ilabel[a]);
+      } else {
+        ++nn;
+      }
+    }
+    st[s] = make_int4(static_cast<int>(n_emit), static_cast<int>(ne),
+                      static_cast<int>(n_eps), static_cast<int>(nn));
+    n_emit += ne;
+    n_eps += nn;
+  }
+  if (n_emit >= 0x7FFFFFFFll || n_eps >= 0x7FFFFFFFll)
+    return Fail(KD_ERR_INVALID, "graph too large (2^31 arcs)");
+  std::vector<int4> ea(static_cast<size_t>(n_emit)), na(static_cast<size_t>(n_eps));
+  {
+    int64_t ie = 0, in = 0;
+    for (int64_t a = 0; a < E; ++a) {
+      int wbits;
+      memcpy(&wbits, &weight[a], 4);
+      if (ilabel[a] != 0)
+        ea[ie++] = make_int4(ilabel[a], wbits, nextstate[a], olabel[a]);
+      else
+        na[in++] = make_int4(olabel[a], wbits, nextstate[a], 0);
+    }
+  }
+  auto *g = new kd_graph;
+  g->device = device;
+  g->num_states = num_states;
+  g->num_arcs = E;
+  g->num_emit = n_emit;
+  g->num_eps = n_eps;
+  g->start = start;
+  g->max_ilabel = max_il;
+  int rc;
+  if ((rc = DevAlloc(&g->st, st.size())) || (rc = DevAlloc(&g->e_arc, ea.size())) ||
+      (rc = DevAlloc(&g->n_arc, na.size())) ||
+      (rc = DevAlloc(&g->fin, static_cast<size_t>(num_states)))) {
+    kd_graph_destroy(g);
+    return rc;
+  }
+  KD_CUDA(cudaMemcpy(g->st, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (!ea.empty())
+    KD_CUDA(cudaMemcpy(g->e_arc, ea.data(), ea.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (!na.empty())
+    KD_CUDA(cudaMemcpy(g->n_arc, na.data(), na.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  KD_CUDA(cudaMemcpy(g->fin, final_weight, sizeof(float) * num_states, cudaMemcpyHostToDevice));
+  *out = g;
+  return KD_OK;
+}
+
+int kd_graph_destroy(kd_graph *g) {
+  if (!g) return KD_OK;
+  cudaSetDevice(g->device);
+  cudaFree(g->st);
+  cudaFree(g->e_arc);
+  cudaFree(g->n_arc);
+  cudaFree(g->fin);
+  delete g;
+  return KD_OK;
+}
+
+int kd_graph_info(const kd_graph *g, int64_t info[5]) {
+  if (!g || !info) return Fail(KD_ERR_INVALID, "null argument");
+  info[0] = g->num_states;
+  info[1] = g->num_arcs;
+  info[2] = g->num_eps;
+  info[3] = g->max_ilabel;
+  info[4] = g->device;
+  return KD_OK;
+}
+
+int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_config *cfg,
+                      kd_decoder **out) {
+  if (!out) return Fail(KD_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!g) return Fail(KD_ERR_INVALID, "graph is null");
+  int rc = CheckOptions(opts);
+  if (rc) return rc;
+  KD_CUDA(cudaSetDevice(g->device));
+  kd_decoder_config c;
+  memset(&c, 0, sizeof(c));
+  if (cfg) c = *cfg;
+  auto *d = new kd_decoder;
+  d->g = g;
+  d->opts = *opts;
+  d->device = g->device;
+  d->max_lanes = c.max_lanes > 0 ? c.max_lanes : 1;
+  cudaDeviceProp prop;
+  KD_CUDA(cudaGetDeviceProperties(&prop, g->device));
+  d->num_sms = prop.multiProcessorCount;
+  uint32_t hcap = c.hash_capacity > 0 ? static_cast<uint32_t>(c.hash_capacity) : (1u << 17);
+  uint32_t p2 = 64;
+  while (p2 < hcap && p2 < (1u << 30)) p2 <<= 1;
+  d->hcap = p2;
+  d->lcap = p2 / 2;
+  d->qcap = p2;
+  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 256 &&
+      c.threads_per_lane != 512) {
+    delete d;
+    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 256 or 512");
+  }
+  d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
+  d->lanes_per_group = c.lanes_per_group > 0 ? c.lanes_per_group : 128;
+
+  const size_t L = static_cast<size_t>(d->max_lanes);
+  const size_t table_bytes_per_lane =
+      static_cast<size_t>(d->hcap) * (4 + 16 + 4) + static_cast<size_t>(d->lcap) * 4 +
+      static_cast<size_t>(d->qcap) * 8;
+  if (c.arena_records > 0) {
+    d->arena_cap = c.arena_records;
+  } else {
+    size_t free_b = 0, total_b = 0;
+    KD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    double budget = 0.5 * static_cast<double>(free_b) - static_cast<double>(table_bytes_per_lane * L);
+    long long per_lane = static_cast<long long>(budget / (20.0 * static_cast<double>(L)));
+    d->arena_cap = std::max<long long>(1 << 16, std::min<long long>(per_lane, 1ll << 25));
+  }
+  if (d->arena_cap > 0xFFFFFFF0ll) d->arena_cap = 0xFFFFFFF0ll;
+
+  const size_t A = static_cast<size_t>(d->arena_cap);
+  if ((rc = DevAlloc(&d->lanes, L)) || (rc = DevAlloc(&d->a_cost, L * A)) ||
+      (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
+      (rc = DevAlloc(&d->hkey, L * d->hcap)) || (rc = DevAlloc(&d->hval, L * d->hcap)) ||
+      (rc = DevAlloc(&d->hidx, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
+      (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->d_items, L)) ||
+      (rc = DevAlloc(&d->d_out_off, L))) {
+    kd_decoder_destroy(d);
+    return rc;
+  }
+  d->n_counters = static_cast<int32_t>(L) + 8;
+  if ((rc = DevAlloc(&d->d_counters, static_cast<size_t>(d->n_counters)))) {
+    kd_decoder_destroy(d);
+    return rc;
+  }
+  d->device_bytes = L * (sizeof(kd::LaneState) + A * 20 + table_bytes_per_lane);
+  KD_CUDA(cudaMemset(d->lanes, 0, L * sizeof(kd::LaneState)));
+  KD_CUDA(cudaMemset(d->hkey, 0xFF, L * d->hcap * sizeof(int32_t)));
+  KD_CUDA(cudaMemset(d->hval, 0xFF, L * d->hcap * sizeof(kd::HVal)));
+  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
+  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
+  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
+  for (int i = 0; i < kNumStreams; ++i) {
+    KD_CUDA(cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking));
+    KD_CUDA(cudaEventCreateWithFlags(&d->ev_stream[i], cudaEventDisableTiming));
+  }
+  KD_CUDA(cudaEventCreate(&d->ev_begin));
+  KD_CUDA(cudaEventCreate(&d->ev_end));
+  d->frames.assign(L, -1);
+  d->status.assign(L, 0);
+  KD_CUDA(cudaDeviceSynchronize());
+  *out = d;
+  return KD_OK;
+}
+
+int kd_decoder_destroy(kd_decoder *d) {
+  if (!d) return KD_OK;
+  cudaSetDevice(d->device);
+  cudaDeviceSynchronize();
+  cudaFree(d->lanes);
+  cudaFree(d->a_cost);
+  cudaFree(d->a_link);
+  cudaFree(d->a_state);
+  cudaFree(d->hkey);
+  cudaFree(d->hval);
+  cudaFree(d->hidx);
+  cudaFree(d->list);
+  cudaFree(d->queue);
+  cudaFree(d->d_items);
+  cudaFree(d->d_counters);
+  cudaFree(d->d_out_off);
+  cudaFree(d->d_stage);
+  cudaFree(d->d_il);
+  cudaFree(d->d_ol);
+  cudaFree(d->d_gw);
+  cudaFree(d->d_aw);
+  if (d->h_items) cudaFreeHost(d->h_items);
+  if (d->h_lanes) cudaFreeHost(d->h_lanes);
+  if (d->h_out_off) cudaFreeHost(d->h_out_off);
+  for (int i = 0; i < kNumStreams; ++i) {
+    if (d->streams[i]) cudaStreamDestroy(d->streams[i]);
+    if (d->ev_stream[i]) cudaEventDestroy(d->ev_stream[i]);
+  }
+  if (d->ev_begin) cudaEventDestroy(d->ev_begin);
+  if (d->ev_end) cudaEventDestroy(d->ev_end);
+  delete d;
+  return KD_OK;
+}
+
+int kd_decoder_set_options(kd_decoder *d, const kd_options *opts) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  int rc = CheckOptions(opts);
+  if (rc) return rc;
+  d->opts = *opts;
+  return KD_OK;
+}
+
+int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
+  int rc = CheckLanes(d, n, lanes);
+  if (rc) return rc;
+  if (n == 0) return KD_OK;
+  KD_CUDA(cudaSetDevice(d->device));
+  cudaStream_t s = d->streams[0];
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t lane = lanes[i];
+    if (d->status[lane] != 0) {
+      // a lane that overflowed may have left claimed table slots behind
+      size_t off = static_cast<size_t>(lane) * d->hcap;
+      KD_CUDA(cudaMemsetAsync(d->hkey + off, 0xFF, d->hcap * sizeof(int32_t), s));
+      KD_CUDA(cudaMemsetAsync(d->hval + off, 0xFF, d->hcap * sizeof(kd::HVal), s));
+      d->status[lane] = 0;
+    }
+    d->h_items[i].lane = lane;
+    d->h_items[i].rows = 0;
+    d->h_items[i].offset = 0;
+    d->h_items[i].target = 0;
+    d->h_items[i].logp = nullptr;
+  }
+  KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
+                          cudaMemcpyHostToDevice, s));
+  kd::Params P = MakeParams(d);
+  P.n_items = n;
+  kd::kd_init_kernel<256><<<n, 256, 0, s>>>(P);
+  KD_CUDA(cudaGetLastError());
+  KD_CUDA(cudaStreamSynchronize(s));
+  rc = FetchLaneStates(d, n, lanes);
+  if (rc) return rc;
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t lane = lanes[i];
+    d->frames[lane] = 0;
+    d->status[lane] = d->h_lanes[lane].status;
+    if (d->status[lane] != 0)
+      return Fail(KD_ERR_OVERFLOW, std::string("InitDecoding: ") + StatusText(d->status[lane]));
+  }
+  return KD_OK;
+}
+
+int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
+                       const float *const *logprobs, const int32_t *rows, int32_t cols,
+                       const int32_t *offsets, int32_t max_num_frames, int mem_kind) {
+  int rc = CheckLanes(d, n, lanes);
+  if (rc) return rc;
+  if (n == 0) return KD_OK;
+  if (!logprobs || !rows) return Fail(KD_ERR_INVALID, "null logprobs/rows");
+  if (mem_kind != KD_MEM_HOST && mem_kind != KD_MEM_DEVICE)
+    return Fail(KD_ERR_INVALID, "bad mem_kind");
+  if (cols < d->g->max_ilabel)
+    return Fail(KD_ERR_INVALID,
+                "decodable has fewer columns than the largest ilabel of the graph "
+                "(the reference would read out of bounds, decodable-ctc.cc:28)");
+  KD_CUDA(cudaSetDevice(d->device));
+  d->last_kernel_ms = 0.f;
+  d->last_launches = 0;
+
+  // per-lane targets (faster-decoder.cc:128-144)
+  struct Work {
+    int32_t lane, target, first_row, n_rows;
+    const float *src;
+  };
+  std::vector<Work> work;
+  work.reserve(n);
+  size_t stage_need = 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const int32_t lane = lanes[i];
+    const int32_t decoded = d->frames[lane];
+    if (decoded < 0)
+      return Fail(KD_ERR_INVALID,
+                  "Check failed!\nx: num_frames_decoded_ >= 0 && \"You must call "
+                  "InitDecoding() before AdvanceDecoding()\"");
+    if (d->status[lane] != 0)
+      return Fail(KD_ERR_OVERFLOW, std::string("lane is in error state: ") +
+                                       StatusText(d->status[lane]));
+    if (rows[i] < 0) return Fail(KD_ERR_INVALID, "negative rows");
+    const int32_t off = offsets ? offsets[i] : 0;
+    const int32_t ready = off + rows[i];
+    if (ready < decoded)
+      return Fail(KD_ERR_INVALID, "Check failed!\nx: num_frames_ready >= num_frames_decoded_");
+    int32_t target = ready;
+    if (max_num_frames >= 0) target = std::min(target, decoded + max_num_frames);
+    if (target <= decoded) continue;
+    if (decoded < off)
+      return Fail(KD_ERR_INVALID, "decodable offset is beyond the frames decoded so far");
+    if (!logprobs[i]) return Fail(KD_ERR_INVALID, "null log-prob matrix");
+    Work w;
+    w.lane = lane;
+    w.target = target;
+    w.first_row = decoded - off;
+    w.n_rows = target - decoded;
+    w.src = logprobs[i] + static_cast<size_t>(w.first_row) * cols;
+    work.push_back(w);
+    stage_need += static_cast<size_t>(w.n_rows) * cols;
+  }
+  if (work.empty()) return KD_OK;
+  const int32_t m = static_cast<int32_t>(work.size());
+
+  kd::Params P = MakeParams(d);
+  P.cols = cols;
+  P.row_in_smem = (static_cast<size_t>(cols) * sizeof(float) <= 32768) ? 1 : 0;
+
+  if (mem_kind == KD_MEM_DEVICE) {
+    for (int32_t i = 0; i < m; ++i) {
+      d->h_items[i].lane = work[i].lane;
+      d->h_items[i].rows = work[i].n_rows;
+      d->h_items[i].offset = d->frames[work[i].lane];
+      d->h_items[i].target = work[i].target;
+      d->h_items[i].logp = work[i].src;
+    }
+    cudaStream_t s = d->streams[0];
+    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
+                            cudaMemcpyHostToDevice, s));
+    KD_CUDA(cudaMemsetAsync(d->d_counters, 0, sizeof(int32_t), s));
+    P.n_items = m;
+    P.work_counter = d->d_counters;
+    KD_CUDA(cudaEventRecord(d->ev_begin, s));
+    rc = LaunchAdvance(d, P, m, PickThreads(d, m), s);
+    if (rc) return rc;
+    KD_CUDA(cudaEventRecord(d->ev_end, s));
+    KD_CUDA(cudaStreamSynchronize(s));
+  } else {
+    // host matrices: stage group by group; copies and searches of different
+    // groups overlap on separate streams.
+    if (stage_need > d->stage_floats) {
+      KD_CUDA(cudaDeviceSynchronize());
+      cudaFree(d->d_stage);
+      d->d_stage = nullptr;
+      d->stage_floats = 0;
+      rc = DevAlloc(&d->d_stage, stage_need);
+      if (rc) return rc;
+      d->stage_floats = stage_need;
+    }
+    const int32_t G = d->lanes_per_group;
+    const int32_t n_groups = (m + G - 1) / G;
+    size_t pos = 0;
+    for (int32_t i = 0; i < m; ++i) {
+      d->h_items[i].lane = work[i].lane;
+      d->h_items[i].rows = work[i].n_rows;
+      d->h_items[i].offset = d->frames[work[i].lane];
+      d->h_items[i].target = work[i].target;
+      d->h_items[i].logp = d->d_stage + pos;
+      pos += static_cast<size_t>(work[i].n_rows) * cols;
+    }
+    cudaStream_t s0 = d->streams[0];
+    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
+                            cudaMemcpyHostToDevice, s0));
+    KD_CUDA(cudaMemsetAsync(d->d_counters, 0,
+                            sizeof(int32_t) * std::min(n_groups, d->n_counters), s0));
+    KD_CUDA(cudaEventRecord(d->ev_begin, s0));
+    for (int i = 1; i < kNumStreams; ++i)
+      KD_CUDA(cudaStreamWaitEvent(d->streams[i], d->ev_begin, 0));
+    const int threads = PickThreads(d, m);
+    for (int32_t gi = 0; gi < n_groups; ++gi) {
+      cudaStream_t s = d->streams[gi % kNumStreams];
+      const int32_t b = gi * G, e = std::min(m, b + G);
+      for (int32_t i = b; i < e; ++i) {
+        KD_CUDA(cudaMemcpyAsync(const_cast<float *>(d->h_items[i].logp), work[i].src,
+                                sizeof(float) * static_cast<size_t>(work[i].n_rows) * cols,
+                                cudaMemcpyHostToDevice, s));
+      }
+      kd::Params Pg = P;
+      Pg.items = d->d_items + b;
+      Pg.n_items = e - b;
+      Pg.work_counter = d->d_counters + (gi % d->n_counters);
+      rc = LaunchAdvance(d, Pg, e - b, threads, s);
+      if (rc) return rc;
+    }
+    for (int i = 1; i < kNumStreams; ++i) {
+      KD_CUDA(cudaEventRecord(d->ev_stream[i], d->streams[i]));
+      KD_CUDA(cudaStreamWaitEvent(s0, d->ev_stream[i], 0));
+    }
+    KD_CUDA(cudaEventRecord(d->ev_end, s0));
+    KD_CUDA(cudaStreamSynchronize(s0));
+  }
+  KD_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev_begin, d->ev_end));
+
+  // status + frame counters
+  std::vector<int32_t> used(m);
+  for (int32_t i = 0; i < m; ++i) used[i] = work[i].lane;
+  rc = FetchLaneStates(d, m, used.data());
+  if (rc) return rc;
+  int bad = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    const int32_t lane = work[i].lane;
+    d->frames[lane] = d->h_lanes[lane].frames_decoded;
+    d->status[lane] = d->h_lanes[lane].status;
+    if (d->status[lane] != 0 && bad == 0) bad = d->status[lane];
+  }
+  if (bad) return Fail(KD_ERR_OVERFLOW, std::string("AdvanceDecoding: ") + StatusText(bad));
+  return KD_OK;
+}
+
+int kd_decoder_num_frames_decoded(kd_decoder *d, int32_t lane, int32_t *out) {
+  int rc = CheckLanes(d, 1, &lane);
+  if (rc) return rc;
+  if (out) *out = d->frames[lane];
+  return KD_OK;
+}
+
+int kd_decoder_best_path_prepare(kd_decoder *d, int32_t n, const int32_t *lanes,
+                                 int use_final_probs, int32_t *ok, int32_t *reached_final,
+                                 int64_t *num_arcs) {
+  int rc = CheckLanes(d, n, lanes);
+  if (rc) return rc;
+  if (n == 0) return KD_OK;
+  KD_CUDA(cudaSetDevice(d->device));
+  for (int32_t i = 0; i < n; ++i) {
+    if (d->frames[lanes[i]] < 0)
+      return Fail(KD_ERR_INVALID, "lane not initialised (call InitDecoding first)");
+    d->h_items[i].lane = lanes[i];
+    d->h_items[i].rows = d->h_items[i].offset = d->h_items[i].target = 0;
+    d->h_items[i].logp = nullptr;
+  }
+  cudaStream_t s = d->streams[0];
+  KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
+                          cudaMemcpyHostToDevice, s));
+  kd::Params P = MakeParams(d);
+  P.n_items = n;
+  kd::kd_best_select_kernel<256><<<n, 256, 0, s>>>(P);
+  KD_CUDA(cudaGetLastError());
+  KD_CUDA(cudaStreamSynchronize(s));
+  rc = FetchLaneStates(d, n, lanes);
+  if (rc) return rc;
+  d->last_use_final = use_final_probs ? 1 : 0;
+  for (int32_t i = 0; i < n; ++i) {
+    const kd::LaneState &L = d->h_lanes[lanes[i]];
+    if (ok) ok[i] = L.bp_ok;
+    if (reached_final) reached_final[i] = L.bp_final;
+    if (num_arcs) num_arcs[i] = L.bp_ok ? L.bp_len : 0;
+  }
+  return KD_OK;
+}
+
+int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
+                               const int64_t *out_offsets, int64_t total_arcs, int32_t *ilabel,
+                               int32_t *olabel, float *graph_cost, float *acoustic_cost,
+                               float *final_weight2) {
+  int rc = CheckLanes(d, n, lanes);
+  if (rc) return rc;
+  if (n == 0) return KD_OK;
+  if (!out_offsets || total_arcs < 0) return Fail(KD_ERR_INVALID, "bad output layout");
+  KD_CUDA(cudaSetDevice(d->device));
+  for (int32_t i = 0; i < n; ++i) {
+    const kd::LaneState &L = d->h_lanes[lanes[i]];
+    if (L.bp_ok && (out_offsets[i] < 0 || out_offsets[i] + L.bp_len > total_arcs))
+      return Fail(KD_ERR_INVALID, "best path does not fit the output arrays");
+    d->h_items[i].lane = lanes[i];
+    d->h_out_off[i] = out_offsets[i];
+    if (final_weight2) {
+      // faster-decoder.cc:416-421
+      const bool fin = L.bp_ok && L.bp_final && d->last_use_final;
+      final_weight2[2 * i] = fin ? L.bp_final_w : 0.f;
+      final_weight2[2 * i + 1] = 0.f;
+    }
+  }
+  if (total_arcs == 0) return KD_OK;
+  if (total_arcs > d->path_cap) {
+    KD_CUDA(cudaDeviceSynchronize());
+    cudaFree(d->d_il);
+    cudaFree(d->d_ol);
+    cudaFree(d->d_gw);
+    cudaFree(d->d_aw);
+    d->d_il = d->d_ol = nullptr;
+    d->d_gw = d->d_aw = nullptr;
+    d->path_cap = 0;
+    size_t cap = static_cast<size_t>(total_arcs) + static_cast<size_t>(total_arcs) / 4 + 1024;
+    if ((rc = DevAlloc(&d->d_il, cap)) || (rc = DevAlloc(&d->d_ol, cap)) ||
+        (rc = DevAlloc(&d->d_gw, cap)) || (rc = DevAlloc(&d->d_aw, cap)))
+      return rc;
+    d->path_cap = static_cast<int64_t>(cap);
+  }
+  cudaStream_t s = d->streams[0];
+  KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
+                          cudaMemcpyHostToDevice, s));
+  KD_CUDA(cudaMemcpyAsync(d->d_out_off, d->h_out_off, sizeof(long long) * n,
+                          cudaMemcpyHostToDevice, s));
+  kd::Params P = MakeParams(d);
+  P.n_items = n;
+  const int tb = 32;
+  kd::kd_best_fill_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(P, d->d_out_off, d->d_il, d->d_ol,
+                                                         d->d_gw, d->d_aw);
+  KD_CUDA(cudaGetLastError());
+  const size_t nb = static_cast<size_t>(total_arcs);
+  if (ilabel)
+    KD_CUDA(cudaMemcpyAsync(ilabel, d->d_il, nb * 4, cudaMemcpyDeviceToHost, s));
+  if (olabel)
+    KD_CUDA(cudaMemcpyAsync(olabel, d->d_ol, nb * 4, cudaMemcpyDeviceToHost, s));
+  if (graph_cost)
+    KD_CUDA(cudaMemcpyAsync(graph_cost, d->d_gw, nb * 4, cudaMemcpyDeviceToHost, s));
+  if (acoustic_cost)
+    KD_CUDA(cudaMemcpyAsync(acoustic_cost, d->d_aw, nb * 4, cudaMemcpyDeviceToHost, s));
+  KD_CUDA(cudaStreamSynchronize(s));
+  return KD_OK;
+}
+
+int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs, int64_t cap,
+                         int32_t *ilabel, int32_t *olabel, float *graph_cost,
+                         float *acoustic_cost, int64_t *num_arcs, float final_weight2[2],
+                         int32_t *reached_final, int32_t *ok) {
+  int32_t okv = 0, rf = 0;
+  int64_t len = 0;
+  int rc = kd_decoder_best_path_prepare(d, 1, &lane, use_final_probs, &okv, &rf, &len);
+  if (rc) return rc;
+  if (num_arcs) *num_arcs = len;
+  if (reached_final) *reached_final = rf;
+  if (ok) *ok = okv;
+  if (final_weight2) final_weight2[0] = final_weight2[1] = 0.f;
+  if (!okv) return KD_OK;
+  if (len > cap) return Fail(KD_ERR_INVALID, "best path longer than the output capacity");
+  int64_t off = 0;
+  return kd_decoder_best_path_fetch(d, 1, &lane, &off, len, ilabel, olabel, graph_cost,
+                                    acoustic_cost, final_weight2);
+}
+
+int kd_decoder_reached_final(kd_decoder *d, int32_t lane, int32_t *out) {
+  int32_t okv = 0, rf = 0;
+  int64_t len = 0;
+  int rc = kd_decoder_best_path_prepare(d, 1, &lane, d ? d->last_use_final : 1, &okv, &rf, &len);
+  if (rc) return rc;
+  if (out) *out = rf;
+  return KD_OK;
+}
+
+int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *states,
+                           double *costs, int64_t *n) {
+  int rc = CheckLanes(d, 1, &lane);
+  if (rc) return rc;
+  KD_CUDA(cudaSetDevice(d->device));
+  if (d->frames[lane] < 0) {
+    if (n) *n = 0;
+    return KD_OK;
+  }
+  rc = FetchLaneStates(d, 1, &lane);
+  if (rc) return rc;
+  const kd::LaneState &L = d->h_lanes[lane];
+  if (n) *n = L.n_tok;
+  if (L.n_tok == 0 || L.n_tok > cap) return KD_OK;
+  const size_t base = static_cast<size_t>(lane) * static_cast<size_t>(d->arena_cap) + L.tok_base;
+  if (states)
+    KD_CUDA(cudaMemcpy(states, d->a_state + base, sizeof(int32_t) * L.n_tok,
+                       cudaMemcpyDeviceToHost));
+  if (costs)
+    KD_CUDA(cudaMemcpy(costs, d->a_cost + base, sizeof(double) * L.n_tok,
+                       cudaMemcpyDeviceToHost));
+  return KD_OK;
+}
+
+int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
+  if (!d || !out) return Fail(KD_ERR_INVALID, "null argument");
+  if (lane >= d->max_lanes) return Fail(KD_ERR_INVALID, "lane id out of range");
+  KD_CUDA(cudaSetDevice(d->device));
+  memset(out, 0, sizeof(*out));
+  KD_CUDA(cudaMemcpy(d->h_lanes, d->lanes, sizeof(kd::LaneState) * d->max_lanes,
+                     cudaMemcpyDeviceToHost));
+  const int32_t lo = lane < 0 ? 0 : lane, hi = lane < 0 ? d->max_lanes : lane + 1;
+  for (int32_t l = lo; l < hi; ++l) {
+    if (d->frames[l] < 0) continue;
+    const kd::LaneState &L = d->h_lanes[l];
+    out->frames += L.st_frames;
+    out->tokens_in += L.st_tokens_in;
+    out->tokens_expanded += L.st_expanded;
+    out->emit_arcs += L.st_emit_arcs;
+    out->eps_arcs += L.st_eps_arcs;
+    out->tokens_out += L.st_tokens_out;
+    out->max_tokens = std::max<int64_t>(out->max_tokens, L.st_max_tokens);
+    out->eps_sweeps += L.st_sweeps;
+  }
+  return KD_OK;
+}
+
+int kd_decoder_last_advance_info(kd_decoder *d, float *kernel_ms, int32_t *launches) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  if (kernel_ms) *kernel_ms = d->last_kernel_ms;
+  if (launches) *launches = d->last_launches;
+  return KD_OK;
+}
+
+int kd_decoder_info(kd_decoder *d, int64_t info[6]) {
+  if (!d || !info) return Fail(KD_ERR_INVALID, "null argument");
+  info[0] = d->max_lanes;
+  info[1] = d->hcap;
+  info[2] = d->arena_cap;
+  info[3] = d->threads;
+  info[4] = static_cast<int64_t>(d->device_bytes);
+  info[5] = d->lanes_per_group;
+  return KD_OK;
+}
+
+}  // extern "C"
