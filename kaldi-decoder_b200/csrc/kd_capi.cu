@@ -75,9 +75,7 @@ struct kd_decoder {
   double *a_cost = nullptr;
   unsigned long long *a_link = nullptr;
   int32_t *a_state = nullptr;
-  int32_t *hkey = nullptr;
-  kd::HVal *hval = nullptr;
-  uint32_t *hidx = nullptr;
+  kd::Entry *table = nullptr;
   uint32_t *list = nullptr;
   uint32_t *queue = nullptr;
   kd::AdvanceItem *d_items = nullptr;
@@ -142,9 +140,7 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.a_link = d->a_link;
   P.a_state = d->a_state;
   P.arena_cap = d->arena_cap;
-  P.hkey = d->hkey;
-  P.hval = d->hval;
-  P.hidx = d->hidx;
+  P.table = d->table;
   P.list = d->list;
   P.queue = d->queue;
   P.hcap = d->hcap;
@@ -153,7 +149,7 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.qcap = d->qcap;
   int lg = 0;
   while ((1u << lg) < d->hcap) ++lg;
-  P.hshift = 32 - lg;
+  P.hshift = 34 - lg;  // (lg - 2) scattered group bits, 2 in-group bits
   return P;
 }
 
@@ -164,16 +160,16 @@ int PickThreads(const kd_decoder *d, int n_items) {
   return 512;
 }
 
-template <int THREADS>
+template <int THREADS, int MIN_BLOCKS>
 int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
-  size_t smem = (THREADS / 32) * 32 * (sizeof(double) + 2 * sizeof(uint32_t));
+  size_t smem = 16;
   if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(float);
   int per_sm = 1;
   KD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, kd::kd_advance_kernel<THREADS>, THREADS, smem));
+      &per_sm, kd::kd_advance_kernel<THREADS, MIN_BLOCKS>, THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = std::min(n_items, per_sm * d->num_sms);
-  kd::kd_advance_kernel<THREADS><<<grid, THREADS, smem, s>>>(P);
+  kd::kd_advance_kernel<THREADS, MIN_BLOCKS><<<grid, THREADS, smem, s>>>(P);
   KD_CUDA(cudaGetLastError());
   d->last_launches++;
   return KD_OK;
@@ -183,13 +179,15 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
                   cudaStream_t s) {
   switch (threads) {
     case 128:
-      return LaunchAdvanceT<128>(d, P, n_items, s);
+      return LaunchAdvanceT<128, 7>(d, P, n_items, s);
+    case 192:
+      return LaunchAdvanceT<192, 5>(d, P, n_items, s);
     case 256:
-      return LaunchAdvanceT<256>(d, P, n_items, s);
+      return LaunchAdvanceT<256, 3>(d, P, n_items, s);
     case 512:
-      return LaunchAdvanceT<512>(d, P, n_items, s);
+      return LaunchAdvanceT<512, 1>(d, P, n_items, s);
     default:
-      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 256 or 512");
+      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 192, 256 or 512");
   }
 }
 
@@ -374,17 +372,17 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->hcap = p2;
   d->lcap = p2 / 2;
   d->qcap = p2;
-  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 256 &&
-      c.threads_per_lane != 512) {
+  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 192 &&
+      c.threads_per_lane != 256 && c.threads_per_lane != 512) {
     delete d;
-    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 256 or 512");
+    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 192, 256 or 512");
   }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
   d->lanes_per_group = c.lanes_per_group > 0 ? c.lanes_per_group : 128;
 
   const size_t L = static_cast<size_t>(d->max_lanes);
   const size_t table_bytes_per_lane =
-      static_cast<size_t>(d->hcap) * (4 + 16 + 4) + static_cast<size_t>(d->lcap) * 4 +
+      static_cast<size_t>(d->hcap) * sizeof(kd::Entry) + static_cast<size_t>(d->lcap) * 4 +
       static_cast<size_t>(d->qcap) * 8;
   if (c.arena_records > 0) {
     d->arena_cap = c.arena_records;
@@ -400,8 +398,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   const size_t A = static_cast<size_t>(d->arena_cap);
   if ((rc = DevAlloc(&d->lanes, L)) || (rc = DevAlloc(&d->a_cost, L * A)) ||
       (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
-      (rc = DevAlloc(&d->hkey, L * d->hcap)) || (rc = DevAlloc(&d->hval, L * d->hcap)) ||
-      (rc = DevAlloc(&d->hidx, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
+      (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
       (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->d_items, L)) ||
       (rc = DevAlloc(&d->d_out_off, L))) {
     kd_decoder_destroy(d);
@@ -414,8 +411,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   }
   d->device_bytes = L * (sizeof(kd::LaneState) + A * 20 + table_bytes_per_lane);
   KD_CUDA(cudaMemset(d->lanes, 0, L * sizeof(kd::LaneState)));
-  KD_CUDA(cudaMemset(d->hkey, 0xFF, L * d->hcap * sizeof(int32_t)));
-  KD_CUDA(cudaMemset(d->hval, 0xFF, L * d->hcap * sizeof(kd::HVal)));
+  KD_CUDA(cudaMemset(d->table, 0xFF, L * d->hcap * sizeof(kd::Entry)));
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
@@ -440,9 +436,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->a_cost);
   cudaFree(d->a_link);
   cudaFree(d->a_state);
-  cudaFree(d->hkey);
-  cudaFree(d->hval);
-  cudaFree(d->hidx);
+  cudaFree(d->table);
   cudaFree(d->list);
   cudaFree(d->queue);
   cudaFree(d->d_items);
@@ -485,8 +479,7 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
     if (d->status[lane] != 0) {
       // a lane that overflowed may have left claimed table slots behind
       size_t off = static_cast<size_t>(lane) * d->hcap;
-      KD_CUDA(cudaMemsetAsync(d->hkey + off, 0xFF, d->hcap * sizeof(int32_t), s));
-      KD_CUDA(cudaMemsetAsync(d->hval + off, 0xFF, d->hcap * sizeof(kd::HVal), s));
+      KD_CUDA(cudaMemsetAsync(d->table + off, 0xFF, d->hcap * sizeof(kd::Entry), s));
       d->status[lane] = 0;
     }
     d->h_items[i].lane = lane;

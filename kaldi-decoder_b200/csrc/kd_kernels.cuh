@@ -52,6 +52,17 @@ struct __align__(16) HVal {
   unsigned long long arg;   // (arc << 32) | prev
 };
 
+// One recombination-table entry = one 32-byte sector: a probe, the 128-bit
+// value CAS, the commit numbering and the wipe of a state all touch the same
+// sector (the first layout used three arrays = three sectors per state and
+// thrashed L2: profiles/r1_v0_ncu_summary.txt).
+struct __align__(32) Entry {
+  HVal val;       // 16-byte aligned: target of the 128-bit CAS
+  int32_t key;    // state id, kEmptyKey when free
+  uint32_t idx;   // commit pass: index of the token in the next block
+  uint32_t pad[2];
+};
+
 // Everything the device keeps per lane between calls.
 struct __align__(16) LaneState {
   int32_t n_tok;           // tokens alive (the reference's toks_ list length)
@@ -102,9 +113,7 @@ struct Params {
   unsigned long long *a_link;
   int32_t *a_state;
   long long arena_cap;
-  int32_t *hkey;
-  HVal *hval;
-  uint32_t *hidx;
+  Entry *table;
   uint32_t *list;
   uint32_t *queue;  // 2 * qcap per lane
   uint32_t hcap, hmask, lcap, qcap;
@@ -237,9 +246,7 @@ struct LaneBuf {
   double *a_cost;
   unsigned long long *a_link;
   int32_t *a_state;
-  int32_t *hkey;
-  HVal *hval;
-  uint32_t *hidx;
+  Entry *table;
   uint32_t *list;
   uint32_t *queue;
 };
@@ -250,9 +257,7 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   b.a_cost = P.a_cost + L * P.arena_cap;
   b.a_link = P.a_link + L * P.arena_cap;
   b.a_state = P.a_state + L * P.arena_cap;
-  b.hkey = P.hkey + L * P.hcap;
-  b.hval = P.hval + L * P.hcap;
-  b.hidx = P.hidx + L * P.hcap;
+  b.table = P.table + L * P.hcap;
   b.list = P.list + L * P.lcap;
   b.queue = P.queue + L * 2 * P.qcap;
   return b;
@@ -262,12 +267,14 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
 // slot is appended to this frame's slot list).  Returns kNoIdx on overflow.
 __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
                                                int32_t state) {
-  uint32_t h = (static_cast<uint32_t>(state) * 0x9E3779B1u) >> P.hshift;
+  // groups of 4 consecutive states share a 128-byte line; groups are scattered
+  uint32_t h = ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
+               (static_cast<uint32_t>(state) & 3u);
   for (uint32_t probe = 0; probe < P.hcap; ++probe) {
-    int32_t k = __ldcg(B.hkey + h);
+    int32_t k = __ldcg(&B.table[h].key);
     if (k == state) return h;
     if (k == kEmptyKey) {
-      int32_t old = atomicCAS(B.hkey + h, kEmptyKey, state);
+      int32_t old = atomicCAS(&B.table[h].key, kEmptyKey, state);
       if (old == kEmptyKey) {
         uint32_t pos = atomicAdd(&sh.list_n, 1u);
         if (pos < P.lcap) {
@@ -387,12 +394,12 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_slot;
-  HVal cur = ld_hval(B.hval + h);
+  HVal cur = ld_hval(&B.table[h].val);
   while (true) {
     bool cur_is_eps = (cur.arg >> 63) != 0;
     bool replace = mine.cost < cur.cost || (!cur_is_eps && !(cur.cost < cstar_key));
     if (!replace) return;
-    HVal got = cas_hval(B.hval + h, cur, mine);
+    HVal got = cas_hval(&B.table[h].val, cur, mine);
     if (got.cost == cur.cost && got.arg == cur.arg) break;
     cur = got;
   }
@@ -408,11 +415,11 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
                                            uint32_t slot, unsigned long long cstar_key,
                                            double cstar, uint32_t *q_next, uint32_t *q_next_n,
                                            unsigned long long *eps_count) {
-  HVal v = ld_hval(B.hval + slot);
+  HVal v = ld_hval(&B.table[slot].val);
   bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(v.cost < cstar_key || is_eps)) return;
-  int32_t state = __ldcg(B.hkey + slot);
+  int32_t state = __ldcg(&B.table[slot].key);
   int4 st = __ldg(P.st + state);
   if (st.w == 0) return;
   double cost = dunkey(v.cost);
@@ -473,7 +480,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     bool live = false;
     if (p < m) {
       h = B.list[p];
-      HVal v = ld_hval(B.hval + h);
+      HVal v = ld_hval(&B.table[h].val);
       live = v.cost != kEmptyCost && (v.cost < cstar_key || (v.arg >> 63) != 0);
     }
     // warp-aggregated numbering: one shared-memory atomic per warp
@@ -484,7 +491,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     if (p < m) {
       uint32_t idx = kNoIdx;
       if (live) idx = wbase + __popc(live_mask & ((1u << (tid & 31)) - 1u));
-      B.hidx[h] = idx;
+      B.table[h].idx = idx;
     }
   }
   __syncthreads();
@@ -500,30 +507,30 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   int my_arg = -1;
   for (uint32_t p = tid; p < m; p += THREADS) {
     uint32_t h = B.list[p];
-    uint32_t idx = B.hidx[h];
+    uint32_t idx = B.table[h].idx;
     if (idx != kNoIdx && write_ok) {
-      HVal v = ld_hval(B.hval + h);
+      HVal v = ld_hval(&B.table[h].val);
       uint32_t arc = static_cast<uint32_t>(v.arg >> 32);
       uint32_t prev = static_cast<uint32_t>(v.arg);
-      if (arc & kEpsFlag) prev = new_base + B.hidx[prev];
+      if (arc & kEpsFlag) prev = new_base + B.table[prev].idx;
       double c = dunkey(v.cost);
       B.a_cost[new_base + idx] = c;
       B.a_link[new_base + idx] = (static_cast<unsigned long long>(arc) << 32) | prev;
-      B.a_state[new_base + idx] = __ldcg(B.hkey + h);
+      B.a_state[new_base + idx] = __ldcg(&B.table[h].key);
       if (c < my_min) {
         my_min = c;
         my_arg = static_cast<int>(idx);
       }
     }
   }
-  __syncthreads();  // every hidx/hkey read above precedes the wipe below
+  __syncthreads();  // every idx/key read above precedes the wipe below
   for (uint32_t p = tid; p < m; p += THREADS) {
     uint32_t h = B.list[p];
-    B.hkey[h] = kEmptyKey;
     ulonglong2 e;
     e.x = kEmptyCost;
     e.y = kEmptyArg;
-    *reinterpret_cast<ulonglong2 *>(B.hval + h) = e;
+    *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = e;
+    B.table[h].key = kEmptyKey;
   }
   double bmin;
   int barg;
@@ -549,13 +556,47 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   __syncthreads();
 }
 
+// The pruned path of one emitting arc: recombine at the destination state.
+__device__ __forceinline__ void emit_insert(const Params &P, const LaneBuf &B, Shared &sh,
+                                         int32_t dst, unsigned long long nk, uint32_t arc,
+                                         uint32_t tok_abs) {
+  uint32_t h = table_slot(P, B, sh, dst);
+  if (h == kNoIdx) return;
+  HVal mine;
+  mine.cost = nk;
+  mine.arg = (static_cast<unsigned long long>(arc) << 32) | tok_abs;
+  table_min(&B.table[h].val, mine);
+}
+
+// One emitting arc (faster-decoder.cc:208-229): new_weight = (w + cost) + ac,
+// admitted against the running cutoff, which it may tighten.
+template <bool ROW_SMEM>
+__device__ __forceinline__ void emit_arc(const Params &P, const LaneBuf &B, Shared &sh,
+                                         const float *row, int4 arc, uint32_t a, double tcost,
+                                         uint32_t tok_abs, double ab) {
+  const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
+  const double nw = (static_cast<double>(__int_as_float(arc.y)) + tcost) + static_cast<double>(-lp);
+  const unsigned long long nk = dkey(nw);
+  const unsigned long long ck = *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key);
+  if (nk < ck) {  // faster-decoder.cc:211
+    const unsigned long long nck = dkey(nw + ab);
+    if (nck < ck) atomicMin(&sh.cut_key, nck);  // faster-decoder.cc:215-217
+    emit_insert(P, B, sh, arc.z, nk, a, tok_abs);
+  }
+}
+
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
-template <int THREADS>
+//
+// Work mapping: a warp takes 32 tokens at a time.  Tokens with few emitting
+// arcs (<= kSmallDeg, the bulk of a lexicon trie) are expanded by their own
+// thread; tokens with many arcs (trie roots, H states) are expanded by the
+// whole warp, 32 consecutive 16-byte arcs per load instruction.
+constexpr uint32_t kSmallDeg = 8;
+
+template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       const LaneState &ls, const float *row_g, float *s_row,
-                                       uint32_t *w_ex, uint32_t *w_beg, double *w_cost) {
-  constexpr int NW = THREADS / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+                                       const LaneState &ls, const float *row_g, float *s_row) {
+  const int tid = threadIdx.x, lane = tid & 31;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const int n = ls.n_tok;
   const uint32_t base = ls.tok_base;
@@ -564,7 +605,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
 
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29)
   const float *row = row_g;
-  if (P.row_in_smem) {
+  if (ROW_SMEM) {
     for (int i = tid; i < P.cols; i += THREADS) s_row[i] = __ldg(row_g + i);
     row = s_row;
   }
@@ -573,8 +614,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     sh.chunk = 0;
   }
   double wc;
-  float ab;
-  lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &ab);
+  float abf;
+  lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &abf);
+  const double ab = static_cast<double>(abf);
   __syncthreads();
 
   // seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189)
@@ -583,9 +625,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     int4 st = __ldg(P.st + state[ls.best_idx]);
     for (int a = tid; a < st.y; a += THREADS) {
       int4 arc = __ldg(P.e_arc + st.x + a);
-      float ac = -row[arc.x - 1];
+      const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
       double nw = (static_cast<double>(__int_as_float(arc.y)) + ls.best_cost) +
-                  static_cast<double>(ac);
+                  static_cast<double>(-lp);
       seed = fmin(seed, nw);
     }
   }
@@ -593,14 +635,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     double smin;
     int dummy;
     block_min_arg<THREADS>(seed, 0, sh, &smin, &dummy);
-    if (tid == 0) sh.cut_key = dkey(smin + static_cast<double>(ab));
+    if (tid == 0) sh.cut_key = dkey(smin + ab);
     __syncthreads();
   }
 
-  // expansion: a warp takes 32 tokens at a time and walks their arcs together
   unsigned long long n_expanded = 0, n_arcs = 0;
-  uint32_t *my_ex = w_ex + warp * 32, *my_beg = w_beg + warp * 32;
-  double *my_cost = w_cost + warp * 32;
   while (true) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(&sh.chunk, 1u);
@@ -620,39 +659,38 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         n_arcs += cnt;
       }
     }
-    uint32_t total;
-    uint32_t ex = warp_excl_scan(cnt, &total);
-    my_ex[lane] = ex;
-    my_beg[lane] = beg;
-    my_cost[lane] = tc;
-    __syncwarp();
-    for (uint32_t j = lane; j < total; j += 32) {
-      // largest t with ex[t] <= j
-      uint32_t t = 0;
+    const bool big = cnt > kSmallDeg;
+    // (i) small tokens: thread-serial, two arcs in flight
+    const uint32_t scnt = big ? 0u : cnt;
+    const uint32_t smax = __reduce_max_sync(0xFFFFFFFFu, scnt);
+    for (uint32_t k = 0; k < smax; k += 2) {
+      const bool p0 = k < scnt, p1 = k + 1 < scnt;
+      int4 a0 = make_int4(1, 0, 0, 0), a1 = make_int4(1, 0, 0, 0);
+      if (p0) a0 = __ldg(P.e_arc + beg + k);
+      if (p1) a1 = __ldg(P.e_arc + beg + k + 1);
+      if (p0) emit_arc<ROW_SMEM>(P, B, sh, row, a0, beg + k, tc, base + i, ab);
+      if (p1) emit_arc<ROW_SMEM>(P, B, sh, row, a1, beg + k + 1, tc, base + i, ab);
+    }
+    // (ii) big tokens: the warp walks the arc range together, 4 loads in flight
+    uint32_t bm = __ballot_sync(0xFFFFFFFFu, big);
+    while (bm) {
+      const int src = __ffs(bm) - 1;
+      bm &= bm - 1;
+      const uint32_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
+      const uint32_t cn = __shfl_sync(0xFFFFFFFFu, cnt, src);
+      const double cst = __shfl_sync(0xFFFFFFFFu, tc, src);
+      const uint32_t tok_abs = base + i0 + src;
+      for (uint32_t j = lane; j < cn; j += 128) {
+        int4 ar[4];
 #pragma unroll
-      for (int s = 16; s; s >>= 1) {
-        if (my_ex[t + s] <= j) t += s;
-      }
-      const uint32_t a = my_beg[t] + (j - my_ex[t]);
-      const int4 arc = __ldg(P.e_arc + a);
-      const float ac = -row[arc.x - 1];
-      const double nw =
-          (static_cast<double>(__int_as_float(arc.y)) + my_cost[t]) + static_cast<double>(ac);
-      const unsigned long long nk = dkey(nw);
-      unsigned long long ck = *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key);
-      if (nk < ck) {  // faster-decoder.cc:211
-        const unsigned long long nck = dkey(nw + static_cast<double>(ab));
-        if (nck < ck) atomicMin(&sh.cut_key, nck);  // faster-decoder.cc:215-217
-        uint32_t h = table_slot(P, B, sh, arc.z);
-        if (h != kNoIdx) {
-          HVal mine;
-          mine.cost = nk;
-          mine.arg = (static_cast<unsigned long long>(a) << 32) | (base + i0 + t);
-          table_min(B.hval + h, mine);
-        }
+        for (int u = 0; u < 4; ++u)
+          if (j + 32u * u < cn) ar[u] = __ldg(P.e_arc + b + j + 32u * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (j + 32u * u < cn)
+            emit_arc<ROW_SMEM>(P, B, sh, row, ar[u], b + j + 32u * u, cst, tok_abs, ab);
       }
     }
-    __syncwarp();
   }
   if (n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
   if (n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
@@ -662,16 +700,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
 
 // ------------------------------------------------------------------ kernels
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) kd_advance_kernel(Params P) {
+template <int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
   __shared__ Shared sh;
   __shared__ LaneState ls;
+  __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
+  const LaneBuf &B = sB;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  constexpr int NW = THREADS / 32;
-  double *w_cost = reinterpret_cast<double *>(dyn_smem);
-  uint32_t *w_ex = reinterpret_cast<uint32_t *>(w_cost + NW * 32);
-  uint32_t *w_beg = w_ex + NW * 32;
-  float *s_row = reinterpret_cast<float *>(w_beg + NW * 32);
+  float *s_row = reinterpret_cast<float *>(dyn_smem);
   const int tid = threadIdx.x;
 
   while (true) {
@@ -680,8 +716,8 @@ __global__ void __launch_bounds__(THREADS) kd_advance_kernel(Params P) {
     const int item = sh.item;
     if (item >= P.n_items) return;
     const AdvanceItem it = P.items[item];
-    const LaneBuf B = lane_buffers(P, it.lane);
     if (tid == 0) {
+      sB = lane_buffers(P, it.lane);
       ls = P.lanes[it.lane];
       sh.status = ls.status;
       sh.list_n = 0;
@@ -692,8 +728,11 @@ __global__ void __launch_bounds__(THREADS) kd_advance_kernel(Params P) {
       const int frame = ls.frames_decoded;
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
       const int n_in = ls.n_tok;
-      double cstar =
-          lane_expand_emitting<THREADS>(P, B, sh, ls, row_g, s_row, w_ex, w_beg, w_cost);
+      double cstar;
+      if (P.row_in_smem)
+        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row);
+      else
+        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row);
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar);
       if (tid == 0) {
         ls.frames_decoded = frame + 1;
@@ -743,7 +782,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     HVal v;
     v.cost = dkey(0.0);
     v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
-    *reinterpret_cast<ulonglong2 *>(B.hval + h) = make_ulonglong2(v.cost, v.arg);
+    *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
   }
   __syncthreads();
   lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */);
