@@ -556,33 +556,77 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   __syncthreads();
 }
 
-// The pruned path of one emitting arc: recombine at the destination state.
-__device__ __forceinline__ void emit_insert(const Params &P, const LaneBuf &B, Shared &sh,
-                                         int32_t dst, unsigned long long nk, uint32_t arc,
-                                         uint32_t tok_abs) {
-  uint32_t h = table_slot(P, B, sh, dst);
+// Admitted emitting arcs are not recombined where they are found: ~97% of the
+// arcs a frame visits fail the pruning test, so a warp iteration over 32 arcs
+// admits about one, and recombining it in place makes 31 lanes wait for one
+// lane's table round trips (profiles/r1_v1_ncu_summary.txt).  Instead each
+// warp parks admitted arcs in a small shared-memory queue and recombines 32 of
+// them at a time, one per lane, so the table latencies overlap.
+struct WarpQueue {
+  unsigned long long nk[64];   // ordered fp64 cost
+  unsigned long long arg[64];  // (arc << 32) | source token
+  int32_t dst[64];             // destination state
+};
+
+__device__ __forceinline__ void queue_insert_one(const Params &P, const LaneBuf &B, Shared &sh,
+                                                 const WarpQueue &q, uint32_t e) {
+  const unsigned long long nk = q.nk[e];
+  // the running cutoff may have tightened since the arc was parked
+  if (!(nk < *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key))) return;
+  uint32_t h = table_slot(P, B, sh, q.dst[e]);
   if (h == kNoIdx) return;
   HVal mine;
   mine.cost = nk;
-  mine.arg = (static_cast<unsigned long long>(arc) << 32) | tok_abs;
+  mine.arg = q.arg[e];
   table_min(&B.table[h].val, mine);
 }
 
+// Warp-convergent: every lane calls it, `adm` says whether this lane parks one.
+__device__ __forceinline__ void queue_push(const Params &P, const LaneBuf &B, Shared &sh,
+                                           WarpQueue &q, uint32_t &qn, bool adm,
+                                           unsigned long long nk, unsigned long long arg,
+                                           int32_t dst) {
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, adm);
+  if (m == 0) return;
+  const uint32_t lane = threadIdx.x & 31;
+  if (adm) {
+    const uint32_t e = qn + __popc(m & ((1u << lane) - 1u));
+    q.nk[e] = nk;
+    q.arg[e] = arg;
+    q.dst[e] = dst;
+  }
+  qn += __popc(m);
+  if (qn >= 32) {
+    __syncwarp();
+    queue_insert_one(P, B, sh, q, qn - 32 + lane);
+    qn -= 32;
+    __syncwarp();
+  }
+}
+
 // One emitting arc (faster-decoder.cc:208-229): new_weight = (w + cost) + ac,
-// admitted against the running cutoff, which it may tighten.
+// tested against the running cutoff (which it may tighten), parked if admitted.
 template <bool ROW_SMEM>
 __device__ __forceinline__ void emit_arc(const Params &P, const LaneBuf &B, Shared &sh,
-                                         const float *row, int4 arc, uint32_t a, double tcost,
-                                         uint32_t tok_abs, double ab) {
-  const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
-  const double nw = (static_cast<double>(__int_as_float(arc.y)) + tcost) + static_cast<double>(-lp);
-  const unsigned long long nk = dkey(nw);
-  const unsigned long long ck = *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key);
-  if (nk < ck) {  // faster-decoder.cc:211
-    const unsigned long long nck = dkey(nw + ab);
-    if (nck < ck) atomicMin(&sh.cut_key, nck);  // faster-decoder.cc:215-217
-    emit_insert(P, B, sh, arc.z, nk, a, tok_abs);
+                                         WarpQueue &q, uint32_t &qn, const float *row, bool valid,
+                                         int4 arc, uint32_t a, double tcost, uint32_t tok_abs,
+                                         double ab, double cut_d) {
+  bool adm = false;
+  unsigned long long nk = 0;
+  if (valid) {
+    const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
+    const double nw =
+        (static_cast<double>(__int_as_float(arc.y)) + tcost) + static_cast<double>(-lp);
+    if (nw < cut_d) {  // faster-decoder.cc:211
+      adm = true;
+      nk = dkey(nw);
+      const unsigned long long nck = dkey(nw + ab);
+      if (nck < *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key))
+        atomicMin(&sh.cut_key, nck);  // faster-decoder.cc:215-217
+    }
   }
+  queue_push(P, B, sh, q, qn, adm, nk, (static_cast<unsigned long long>(a) << 32) | tok_abs,
+             arc.z);
 }
 
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
@@ -595,13 +639,16 @@ constexpr uint32_t kSmallDeg = 8;
 
 template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       const LaneState &ls, const float *row_g, float *s_row) {
+                                       const LaneState &ls, const float *row_g, float *s_row,
+                                       WarpQueue *queues) {
   const int tid = threadIdx.x, lane = tid & 31;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const int n = ls.n_tok;
   const uint32_t base = ls.tok_base;
   const double *cost = B.a_cost + base;
   const int32_t *state = B.a_state + base;
+  WarpQueue &q = queues[tid >> 5];
+  uint32_t qn = 0;
 
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29)
   const float *row = row_g;
@@ -668,8 +715,10 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       int4 a0 = make_int4(1, 0, 0, 0), a1 = make_int4(1, 0, 0, 0);
       if (p0) a0 = __ldg(P.e_arc + beg + k);
       if (p1) a1 = __ldg(P.e_arc + beg + k + 1);
-      if (p0) emit_arc<ROW_SMEM>(P, B, sh, row, a0, beg + k, tc, base + i, ab);
-      if (p1) emit_arc<ROW_SMEM>(P, B, sh, row, a1, beg + k + 1, tc, base + i, ab);
+      const double cut_d =
+          dunkey(*reinterpret_cast<volatile unsigned long long *>(&sh.cut_key));
+      emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, p0, a0, beg + k, tc, base + i, ab, cut_d);
+      emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, p1, a1, beg + k + 1, tc, base + i, ab, cut_d);
     }
     // (ii) big tokens: the warp walks the arc range together, 4 loads in flight
     uint32_t bm = __ballot_sync(0xFFFFFFFFu, big);
@@ -680,18 +729,28 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       const uint32_t cn = __shfl_sync(0xFFFFFFFFu, cnt, src);
       const double cst = __shfl_sync(0xFFFFFFFFu, tc, src);
       const uint32_t tok_abs = base + i0 + src;
-      for (uint32_t j = lane; j < cn; j += 128) {
+      for (uint32_t j0 = 0; j0 < cn; j0 += 128) {
         int4 ar[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (j + 32u * u < cn) ar[u] = __ldg(P.e_arc + b + j + 32u * u);
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + 32u * u + lane;
+          ar[u] = make_int4(1, 0, 0, 0);
+          if (j < cn) ar[u] = __ldg(P.e_arc + b + j);
+        }
+        const double cut_d =
+            dunkey(*reinterpret_cast<volatile unsigned long long *>(&sh.cut_key));
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (j + 32u * u < cn)
-            emit_arc<ROW_SMEM>(P, B, sh, row, ar[u], b + j + 32u * u, cst, tok_abs, ab);
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t j = j0 + 32u * u + lane;
+          emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, j < cn, ar[u], b + j, cst, tok_abs, ab,
+                             cut_d);
+        }
       }
     }
   }
+  // recombine what is still parked
+  __syncwarp();
+  if (lane < qn) queue_insert_one(P, B, sh, q, lane);
   if (n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
   if (n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
   __syncthreads();
@@ -706,6 +765,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
   __shared__ LaneState ls;
   __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
   const LaneBuf &B = sB;
+  __shared__ WarpQueue queues[THREADS / 32];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   float *s_row = reinterpret_cast<float *>(dyn_smem);
   const int tid = threadIdx.x;
@@ -730,9 +790,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       const int n_in = ls.n_tok;
       double cstar;
       if (P.row_in_smem)
-        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row);
+        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row, queues);
       else
-        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row);
+        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, queues);
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar);
       if (tid == 0) {
         ls.frames_decoded = frame + 1;
