@@ -81,6 +81,11 @@ typedef struct kd_stats {
   int64_t tokens_out;      /* tokens alive at frame end                           */
   int64_t max_tokens;      /* max tokens alive at a frame end                     */
   int64_t eps_sweeps;      /* closure sweeps                                      */
+  /* SM cycles per phase (clock64 of the lane's thread 0, summed over frames) */
+  int64_t cycles_cutoff;   /* GetCutoff + row staging + seed                      */
+  int64_t cycles_expand;   /* emitting expansion + recombination                  */
+  int64_t cycles_closure;  /* epsilon closure                                     */
+  int64_t cycles_commit;   /* token block commit + table wipe                     */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

@@ -162,8 +162,12 @@ int PickThreads(const kd_decoder *d, int n_items) {
 
 template <int THREADS, int MIN_BLOCKS>
 int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
-  size_t smem = 16;
+  size_t smem = (THREADS / 32) * sizeof(kd::WarpQueue) + 16;
   if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(float);
+  if (smem > 48 * 1024)
+    KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
   int per_sm = 1;
   KD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
       &per_sm, kd::kd_advance_kernel<THREADS, MIN_BLOCKS>, THREADS, smem));
@@ -834,6 +838,10 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->tokens_out += L.st_tokens_out;
     out->max_tokens = std::max<int64_t>(out->max_tokens, L.st_max_tokens);
     out->eps_sweeps += L.st_sweeps;
+    out->cycles_cutoff += L.cyc_cutoff;
+    out->cycles_expand += L.cyc_expand;
+    out->cycles_closure += L.cyc_closure;
+    out->cycles_commit += L.cyc_commit;
   }
   return KD_OK;
 }

@@ -75,6 +75,8 @@ struct __align__(16) LaneState {
   // counters (kd_stats)
   long long st_frames, st_tokens_in, st_expanded, st_emit_arcs, st_eps_arcs,
       st_tokens_out, st_max_tokens, st_sweeps;
+  // SM cycles spent per phase (clock64 of thread 0), for the phase breakdown
+  long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit;
   // best-path selection results
   int32_t bp_ok, bp_final, bp_best_state;
   uint32_t bp_best_tok;    // arena index
@@ -184,16 +186,18 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t *total) 
 }
 
 struct Shared {
-  unsigned long long cut_key;  // running next-frame cutoff, then C*
-  unsigned long long acc_emit, acc_eps, acc_expanded;
+  double cstar;                // C* of the frame being processed
   double red_d[32];
   int red_i[32];
   uint32_t hist[256];
+  uint32_t cut_fkey;  // running next-frame cutoff, rounded UP to float (a filter only)
+  uint32_t acc_emit, acc_eps, acc_expanded;  // per-frame counters
   uint32_t list_n;
   uint32_t q_n[2];
   uint32_t out_n;
   uint32_t chunk;
   uint32_t sel_bin, sel_k;
+  long long t_mark;
   int status;
   int item;
 };
@@ -414,7 +418,7 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
 __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Shared &sh,
                                            uint32_t slot, unsigned long long cstar_key,
                                            double cstar, uint32_t *q_next, uint32_t *q_next_n,
-                                           unsigned long long *eps_count) {
+                                           uint32_t *eps_count) {
   HVal v = ld_hval(&B.table[slot].val);
   bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
@@ -423,7 +427,7 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   int4 st = __ldg(P.st + state);
   if (st.w == 0) return;
   double cost = dunkey(v.cost);
-  *eps_count += static_cast<unsigned long long>(st.w);
+  *eps_count += static_cast<uint32_t>(st.w);
   for (int a = st.z; a < st.z + st.w; ++a) {
     int4 arc = __ldg(P.n_arc + a);
     double nc = cost + static_cast<double>(__int_as_float(arc.y));
@@ -442,14 +446,16 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   const int tid = threadIdx.x;
   const unsigned long long cstar_key = dkey(cstar);
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  const long long t_begin = clock64();
   // ---- closure: sweep 0 expands every token, later sweeps the improved ones
   if (tid == 0) {
     sh.q_n[0] = 0;
     sh.q_n[1] = 0;
     sh.out_n = 0;
+    sh.acc_eps = 0;
   }
   __syncthreads();
-  unsigned long long eps_count = 0;
+  uint32_t eps_count = 0;
   const uint32_t m0 = min(sh.list_n, P.lcap);
   __syncthreads();  // everyone holds m0 before the closure starts growing the list
   uint32_t *q0 = B.queue, *q1 = B.queue + P.qcap;
@@ -472,6 +478,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     ++sweeps;
   }
   __syncthreads();
+  const long long t_mid = clock64();
   // ---- commit, pass 1: number the live entries
   const uint32_t m = min(sh.list_n, P.lcap);
   for (uint32_t p0 = 0; p0 < m; p0 += THREADS) {  // uniform trip count: full-warp ballots
@@ -536,7 +543,8 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   int barg;
   block_min_arg<THREADS>(my_min, my_arg, sh, &bmin, &barg);
   // accumulate counters
-  if (eps_count) atomicAdd(&sh.acc_eps, eps_count);
+  eps_count = __reduce_add_sync(0xFFFFFFFFu, eps_count);
+  if ((tid & 31) == 0 && eps_count) atomicAdd(&sh.acc_eps, eps_count);
   __syncthreads();
   if (tid == 0) {
     if (write_ok) {
@@ -551,6 +559,9 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.best_idx = -1;
     }
     ls.st_sweeps += sweeps;
+    ls.st_eps_arcs += sh.acc_eps;
+    ls.cyc_closure += t_mid - t_begin;
+    ls.cyc_commit += clock64() - t_mid;
     sh.list_n = 0;
   }
   __syncthreads();
@@ -560,19 +571,26 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
 // arcs a frame visits fail the pruning test, so a warp iteration over 32 arcs
 // admits about one, and recombining it in place makes 31 lanes wait for one
 // lane's table round trips (profiles/r1_v1_ncu_summary.txt).  Instead each
-// warp parks admitted arcs in a small shared-memory queue and recombines 32 of
-// them at a time, one per lane, so the table latencies overlap.
+// warp parks admitted arcs in a shared-memory queue (one native 32-bit
+// shared-memory atomicAdd per admitted arc, nothing per rejected arc) and
+// recombines 32 of them at a time, one per lane, so the table latencies overlap.
+constexpr uint32_t kQueueCap = 192;  // 31 left over + at most 4 x 32 parked between checks
+
 struct WarpQueue {
-  unsigned long long nk[64];   // ordered fp64 cost
-  unsigned long long arg[64];  // (arc << 32) | source token
-  int32_t dst[64];             // destination state
+  unsigned long long nk[kQueueCap];   // ordered fp64 cost
+  unsigned long long arg[kQueueCap];  // (arc << 32) | source token
+  int32_t dst[kQueueCap];             // destination state
+  uint32_t n;
+  uint32_t pad[3];
 };
 
 __device__ __forceinline__ void queue_insert_one(const Params &P, const LaneBuf &B, Shared &sh,
                                                  const WarpQueue &q, uint32_t e) {
   const unsigned long long nk = q.nk[e];
   // the running cutoff may have tightened since the arc was parked
-  if (!(nk < *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key))) return;
+  const double cut_now =
+      static_cast<double>(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
+  if (!(dunkey(nk) < cut_now)) return;
   uint32_t h = table_slot(P, B, sh, q.dst[e]);
   if (h == kNoIdx) return;
   HVal mine;
@@ -581,52 +599,60 @@ __device__ __forceinline__ void queue_insert_one(const Params &P, const LaneBuf 
   table_min(&B.table[h].val, mine);
 }
 
-// Warp-convergent: every lane calls it, `adm` says whether this lane parks one.
-__device__ __forceinline__ void queue_push(const Params &P, const LaneBuf &B, Shared &sh,
-                                           WarpQueue &q, uint32_t &qn, bool adm,
-                                           unsigned long long nk, unsigned long long arg,
-                                           int32_t dst) {
-  const uint32_t m = __ballot_sync(0xFFFFFFFFu, adm);
-  if (m == 0) return;
-  const uint32_t lane = threadIdx.x & 31;
-  if (adm) {
-    const uint32_t e = qn + __popc(m & ((1u << lane) - 1u));
-    q.nk[e] = nk;
-    q.arg[e] = arg;
-    q.dst[e] = dst;
-  }
-  qn += __popc(m);
-  if (qn >= 32) {
-    __syncwarp();
-    queue_insert_one(P, B, sh, q, qn - 32 + lane);
-    qn -= 32;
-    __syncwarp();
-  }
+// Warp-convergent: recombines full groups of 32 parked arcs.
+__device__ __forceinline__ void queue_drain_full(const Params &P, const LaneBuf &B, Shared &sh,
+                                                 WarpQueue &q) {
+  uint32_t n = *reinterpret_cast<volatile uint32_t *>(&q.n);
+  if (n < 32) return;  // q.n is only written by this warp: the value is warp-uniform
+  __syncwarp();
+  do {
+    queue_insert_one(P, B, sh, q, n - 32 + (threadIdx.x & 31));
+    n -= 32;
+  } while (n >= 32);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) q.n = n;
+  __syncwarp();
 }
 
-// One emitting arc (faster-decoder.cc:208-229): new_weight = (w + cost) + ac,
-// tested against the running cutoff (which it may tighten), parked if admitted.
+// Four emitting arcs per thread (faster-decoder.cc:208-229): new_weight =
+// (w + cost) + ac for all four first -- straight-line code the compiler can
+// interleave -- then the rare admitted ones are parked.  The shared running
+// cutoff is kept as a float rounded UP (one native 32-bit shared-memory
+// atomicMin); it only filters.  The exact C* comes from the per-thread fp64
+// minimum `my_min` reduced at the end of the frame: the arc with the globally
+// smallest new_weight always passes the filter.  Slots with bit u of `vmask`
+// clear hold a dummy arc (ilabel 1) and are ignored.
 template <bool ROW_SMEM>
-__device__ __forceinline__ void emit_arc(const Params &P, const LaneBuf &B, Shared &sh,
-                                         WarpQueue &q, uint32_t &qn, const float *row, bool valid,
-                                         int4 arc, uint32_t a, double tcost, uint32_t tok_abs,
-                                         double ab, double cut_d) {
-  bool adm = false;
-  unsigned long long nk = 0;
-  if (valid) {
-    const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
-    const double nw =
-        (static_cast<double>(__int_as_float(arc.y)) + tcost) + static_cast<double>(-lp);
-    if (nw < cut_d) {  // faster-decoder.cc:211
-      adm = true;
-      nk = dkey(nw);
-      const unsigned long long nck = dkey(nw + ab);
-      if (nck < *reinterpret_cast<volatile unsigned long long *>(&sh.cut_key))
-        atomicMin(&sh.cut_key, nck);  // faster-decoder.cc:215-217
+__device__ __forceinline__ void emit4(Shared &sh, WarpQueue &q, const float *row,
+                                      const int4 (&ar)[4], uint32_t vmask, uint32_t a0,
+                                      uint32_t a_stride, double tcost, uint32_t tok_abs,
+                                      double ab, double &my_min) {
+  const double cut_d =
+      static_cast<double>(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
+  double nw[4];
+  uint32_t adm = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float lp = ROW_SMEM ? row[ar[u].x - 1] : __ldg(row + ar[u].x - 1);
+    nw[u] = (static_cast<double>(__int_as_float(ar[u].y)) + tcost) + static_cast<double>(-lp);
+    if (nw[u] < cut_d) adm |= 1u << u;  // faster-decoder.cc:211 (filter; exact test at commit)
+  }
+  adm &= vmask;
+  if (adm == 0) return;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (adm & (1u << u)) {
+      const uint32_t e = atomicAdd(&q.n, 1u);
+      q.nk[e] = dkey(nw[u]);
+      q.arg[e] = (static_cast<unsigned long long>(a0 + a_stride * u) << 32) | tok_abs;
+      q.dst[e] = ar[u].z;
+      if (nw[u] < my_min) {
+        my_min = nw[u];
+        const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));  // faster-decoder.cc:215-217
+        if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)) atomicMin(&sh.cut_fkey, fk);
+      }
     }
   }
-  queue_push(P, B, sh, q, qn, adm, nk, (static_cast<unsigned long long>(a) << 32) | tok_abs,
-             arc.z);
 }
 
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
@@ -639,7 +665,7 @@ constexpr uint32_t kSmallDeg = 8;
 
 template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       const LaneState &ls, const float *row_g, float *s_row,
+                                       LaneState &ls, const float *row_g, float *s_row,
                                        WarpQueue *queues) {
   const int tid = threadIdx.x, lane = tid & 31;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
@@ -648,7 +674,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   const double *cost = B.a_cost + base;
   const int32_t *state = B.a_state + base;
   WarpQueue &q = queues[tid >> 5];
-  uint32_t qn = 0;
+  const long long t_begin = clock64();
 
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29)
   const float *row = row_g;
@@ -657,8 +683,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     row = s_row;
   }
   if (tid == 0) {
-    sh.cut_key = dkey(inf);
+    sh.cut_fkey = fkey(__int_as_float(0x7F800000));
     sh.chunk = 0;
+    sh.acc_emit = sh.acc_expanded = 0;
   }
   double wc;
   float abf;
@@ -682,11 +709,15 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     double smin;
     int dummy;
     block_min_arg<THREADS>(seed, 0, sh, &smin, &dummy);
-    if (tid == 0) sh.cut_key = dkey(smin + ab);
+    if (tid == 0) sh.cut_fkey = fkey(__double2float_ru(smin + ab));
     __syncthreads();
   }
+  if (tid == 0) sh.t_mark = clock64();
 
-  unsigned long long n_expanded = 0, n_arcs = 0;
+  uint32_t n_expanded = 0, n_arcs = 0;
+  double my_min = inf;
+  if (lane == 0) q.n = 0;
+  __syncwarp();
   while (true) {
     uint32_t c = 0;
     if (lane == 0) c = atomicAdd(&sh.chunk, 1u);
@@ -707,20 +738,25 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       }
     }
     const bool big = cnt > kSmallDeg;
-    // (i) small tokens: thread-serial, two arcs in flight
+    // (i) small tokens: each thread walks its own arcs, 4 at a time
     const uint32_t scnt = big ? 0u : cnt;
-    const uint32_t smax = __reduce_max_sync(0xFFFFFFFFu, scnt);
-    for (uint32_t k = 0; k < smax; k += 2) {
-      const bool p0 = k < scnt, p1 = k + 1 < scnt;
-      int4 a0 = make_int4(1, 0, 0, 0), a1 = make_int4(1, 0, 0, 0);
-      if (p0) a0 = __ldg(P.e_arc + beg + k);
-      if (p1) a1 = __ldg(P.e_arc + beg + k + 1);
-      const double cut_d =
-          dunkey(*reinterpret_cast<volatile unsigned long long *>(&sh.cut_key));
-      emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, p0, a0, beg + k, tc, base + i, ab, cut_d);
-      emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, p1, a1, beg + k + 1, tc, base + i, ab, cut_d);
+#pragma unroll 1
+    for (uint32_t k0 = 0; k0 < kSmallDeg; k0 += 4) {
+      if (!__any_sync(0xFFFFFFFFu, k0 < scnt)) break;
+      int4 ar[4];
+      uint32_t vmask = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ar[u] = make_int4(1, 0, 0, 0);
+        if (k0 + u < scnt) {
+          ar[u] = __ldg(P.e_arc + beg + k0 + u);
+          vmask |= 1u << u;
+        }
+      }
+      emit4<ROW_SMEM>(sh, q, row, ar, vmask, beg + k0, 1u, tc, base + i, ab, my_min);
+      queue_drain_full(P, B, sh, q);
     }
-    // (ii) big tokens: the warp walks the arc range together, 4 loads in flight
+    // (ii) big tokens: the warp walks the arc range together, 4 x 32 arcs per step
     uint32_t bm = __ballot_sync(0xFFFFFFFFu, big);
     while (bm) {
       const int src = __ffs(bm) - 1;
@@ -729,32 +765,41 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       const uint32_t cn = __shfl_sync(0xFFFFFFFFu, cnt, src);
       const double cst = __shfl_sync(0xFFFFFFFFu, tc, src);
       const uint32_t tok_abs = base + i0 + src;
+#pragma unroll 1
       for (uint32_t j0 = 0; j0 < cn; j0 += 128) {
         int4 ar[4];
+        uint32_t vmask = 0;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint32_t j = j0 + 32u * u + lane;
           ar[u] = make_int4(1, 0, 0, 0);
-          if (j < cn) ar[u] = __ldg(P.e_arc + b + j);
+          if (j < cn) {
+            ar[u] = __ldg(P.e_arc + b + j);
+            vmask |= 1u << u;
+          }
         }
-        const double cut_d =
-            dunkey(*reinterpret_cast<volatile unsigned long long *>(&sh.cut_key));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t j = j0 + 32u * u + lane;
-          emit_arc<ROW_SMEM>(P, B, sh, q, qn, row, j < cn, ar[u], b + j, cst, tok_abs, ab,
-                             cut_d);
-        }
+        emit4<ROW_SMEM>(sh, q, row, ar, vmask, b + j0 + lane, 32u, cst, tok_abs, ab, my_min);
+        queue_drain_full(P, B, sh, q);
       }
     }
   }
   // recombine what is still parked
   __syncwarp();
-  if (lane < qn) queue_insert_one(P, B, sh, q, lane);
-  if (n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
-  if (n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
-  __syncthreads();
-  return dunkey(sh.cut_key);
+  if (lane < *reinterpret_cast<volatile uint32_t *>(&q.n)) queue_insert_one(P, B, sh, q, lane);
+  n_expanded = __reduce_add_sync(0xFFFFFFFFu, n_expanded);
+  n_arcs = __reduce_add_sync(0xFFFFFFFFu, n_arcs);
+  if (lane == 0 && n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
+  if (lane == 0 && n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
+  // exact C* = min(new_weight) + adaptive_beam (faster-decoder.cc:240), including the seed
+  double bmin;
+  int dummy2;
+  block_min_arg<THREADS>(fmin(my_min, seed), 0, sh, &bmin, &dummy2);
+  if (tid == 0) {
+    const long long t_end = clock64();
+    ls.cyc_cutoff += sh.t_mark - t_begin;
+    ls.cyc_expand += t_end - sh.t_mark;
+  }
+  return bmin + ab;
 }
 
 // ------------------------------------------------------------------ kernels
@@ -765,9 +810,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
   __shared__ LaneState ls;
   __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
   const LaneBuf &B = sB;
-  __shared__ WarpQueue queues[THREADS / 32];
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  float *s_row = reinterpret_cast<float *>(dyn_smem);
+  WarpQueue *queues = reinterpret_cast<WarpQueue *>(dyn_smem);
+  float *s_row = reinterpret_cast<float *>(dyn_smem + (THREADS / 32) * sizeof(WarpQueue));
   const int tid = threadIdx.x;
 
   while (true) {
@@ -781,7 +826,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       ls = P.lanes[it.lane];
       sh.status = ls.status;
       sh.list_n = 0;
-      sh.acc_emit = sh.acc_eps = sh.acc_expanded = 0;
     }
     __syncthreads();
     while (ls.frames_decoded < it.target && sh.status == 0) {
@@ -799,15 +843,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
         ls.st_frames += 1;
         ls.st_tokens_in += n_in;
         ls.st_tokens_out += ls.n_tok;
+        ls.st_emit_arcs += sh.acc_emit;
+        ls.st_expanded += sh.acc_expanded;
         if (ls.n_tok > ls.st_max_tokens) ls.st_max_tokens = ls.n_tok;
       }
       __syncthreads();
     }
     if (tid == 0) {
       ls.status = sh.status;
-      ls.st_emit_arcs += static_cast<long long>(sh.acc_emit);
-      ls.st_eps_arcs += static_cast<long long>(sh.acc_eps);
-      ls.st_expanded += static_cast<long long>(sh.acc_expanded);
       P.lanes[it.lane] = ls;
     }
     __syncthreads();
@@ -834,7 +877,6 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     ls = z;
     sh.status = 0;
     sh.list_n = 0;
-    sh.acc_emit = sh.acc_eps = sh.acc_expanded = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -849,6 +891,8 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
   if (tid == 0) {
     ls.status = sh.status;
     ls.st_sweeps = 0;
+    ls.st_eps_arcs = 0;
+    ls.cyc_closure = ls.cyc_commit = 0;
     P.lanes[lane] = ls;
   }
 }
