@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -54,7 +55,8 @@ struct kd_graph {
   int64_t num_states = 0, num_arcs = 0, num_emit = 0, num_eps = 0;
   int32_t start = -1, max_ilabel = 0;
   int4 *st = nullptr;
-  int4 *e_arc = nullptr;
+  int2 *e_iw = nullptr;
+  int2 *e_no = nullptr;
   int4 *n_arc = nullptr;
   float *fin = nullptr;
 };
@@ -65,7 +67,7 @@ struct kd_decoder {
   int device = 0;
   int num_sms = kNumSMsFallback;
   int32_t max_lanes = 1;
-  uint32_t hcap = 0, lcap = 0, qcap = 0;
+  uint32_t hcap = 0, lcap = 0, qcap = 0, ccap = 0;
   int64_t arena_cap = 0;
   int32_t threads = 0;  // 0 = auto per launch
   int32_t lanes_per_group = 128;
@@ -78,6 +80,7 @@ struct kd_decoder {
   kd::Entry *table = nullptr;
   uint32_t *list = nullptr;
   uint32_t *queue = nullptr;
+  uint4 *cand = nullptr;
   kd::AdvanceItem *d_items = nullptr;
   int32_t *d_counters = nullptr;  // one per launch slot
   int32_t n_counters = 0;
@@ -126,7 +129,8 @@ kd::Params MakeParams(const kd_decoder *d) {
   kd::Params P;
   memset(&P, 0, sizeof(P));
   P.st = d->g->st;
-  P.e_arc = d->g->e_arc;
+  P.e_iw = d->g->e_iw;
+  P.e_no = d->g->e_no;
   P.n_arc = d->g->n_arc;
   P.fin = d->g->fin;
   P.start = d->g->start;
@@ -143,6 +147,8 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.table = d->table;
   P.list = d->list;
   P.queue = d->queue;
+  P.cand = d->cand;
+  P.ccap = d->ccap;
   P.hcap = d->hcap;
   P.hmask = d->hcap - 1;
   P.lcap = d->lcap;
@@ -162,8 +168,8 @@ int PickThreads(const kd_decoder *d, int n_items) {
 
 template <int THREADS, int MIN_BLOCKS>
 int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
-  size_t smem = (THREADS / 32) * sizeof(kd::WarpQueue) + 16;
-  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(float);
+  size_t smem = kd::advance_smem_fixed<THREADS>() + 16;
+  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(double);
   if (smem > 48 * 1024)
     KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -293,16 +299,23 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   }
   if (n_emit >= 0x7FFFFFFFll || n_eps >= 0x7FFFFFFFll)
     return Fail(KD_ERR_INVALID, "graph too large (2^31 arcs)");
-  std::vector<int4> ea(static_cast<size_t>(n_emit)), na(static_cast<size_t>(n_eps));
+  // (nextstate | kEpsFlag) marks destinations that have epsilon arcs of their own
+  std::vector<int2> eiw(static_cast<size_t>(n_emit)), eno(static_cast<size_t>(n_emit));
+  std::vector<int4> na(static_cast<size_t>(n_eps));
   {
     int64_t ie = 0, in = 0;
     for (int64_t a = 0; a < E; ++a) {
       int wbits;
       memcpy(&wbits, &weight[a], 4);
-      if (ilabel[a] != 0)
-        ea[ie++] = make_int4(ilabel[a], wbits, nextstate[a], olabel[a]);
-      else
-        na[in++] = make_int4(olabel[a], wbits, nextstate[a], 0);
+      const int32_t ns = nextstate[a];
+      const int ns_word = st[ns].w > 0 ? static_cast<int>(static_cast<uint32_t>(ns) | kd::kEpsFlag) : ns;
+      if (ilabel[a] != 0) {
+        eiw[ie] = make_int2(ilabel[a], wbits);
+        eno[ie] = make_int2(ns_word, olabel[a]);
+        ++ie;
+      } else {
+        na[in++] = make_int4(olabel[a], wbits, ns_word, 0);
+      }
     }
   }
   auto *g = new kd_graph;
@@ -314,15 +327,17 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   g->start = start;
   g->max_ilabel = max_il;
   int rc;
-  if ((rc = DevAlloc(&g->st, st.size())) || (rc = DevAlloc(&g->e_arc, ea.size())) ||
-      (rc = DevAlloc(&g->n_arc, na.size())) ||
+  if ((rc = DevAlloc(&g->st, st.size())) || (rc = DevAlloc(&g->e_iw, eiw.size())) ||
+      (rc = DevAlloc(&g->e_no, eno.size())) || (rc = DevAlloc(&g->n_arc, na.size())) ||
       (rc = DevAlloc(&g->fin, static_cast<size_t>(num_states)))) {
     kd_graph_destroy(g);
     return rc;
   }
   KD_CUDA(cudaMemcpy(g->st, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  if (!ea.empty())
-    KD_CUDA(cudaMemcpy(g->e_arc, ea.data(), ea.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  if (!eiw.empty()) {
+    KD_CUDA(cudaMemcpy(g->e_iw, eiw.data(), eiw.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    KD_CUDA(cudaMemcpy(g->e_no, eno.data(), eno.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  }
   if (!na.empty())
     KD_CUDA(cudaMemcpy(g->n_arc, na.data(), na.size() * sizeof(int4), cudaMemcpyHostToDevice));
   KD_CUDA(cudaMemcpy(g->fin, final_weight, sizeof(float) * num_states, cudaMemcpyHostToDevice));
@@ -334,7 +349,8 @@ int kd_graph_destroy(kd_graph *g) {
   if (!g) return KD_OK;
   cudaSetDevice(g->device);
   cudaFree(g->st);
-  cudaFree(g->e_arc);
+  cudaFree(g->e_iw);
+  cudaFree(g->e_no);
   cudaFree(g->n_arc);
   cudaFree(g->fin);
   delete g;
@@ -376,6 +392,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->hcap = p2;
   d->lcap = p2 / 2;
   d->qcap = p2;
+  d->ccap = p2 / 4;
   if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 192 &&
       c.threads_per_lane != 256 && c.threads_per_lane != 512) {
     delete d;
@@ -387,7 +404,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   const size_t L = static_cast<size_t>(d->max_lanes);
   const size_t table_bytes_per_lane =
       static_cast<size_t>(d->hcap) * sizeof(kd::Entry) + static_cast<size_t>(d->lcap) * 4 +
-      static_cast<size_t>(d->qcap) * 8;
+      static_cast<size_t>(d->qcap) * 8 + static_cast<size_t>(d->ccap) * 16;
   if (c.arena_records > 0) {
     d->arena_cap = c.arena_records;
   } else {
@@ -403,7 +420,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   if ((rc = DevAlloc(&d->lanes, L)) || (rc = DevAlloc(&d->a_cost, L * A)) ||
       (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
       (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
-      (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->d_items, L)) ||
+      (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) || (rc = DevAlloc(&d->d_items, L)) ||
       (rc = DevAlloc(&d->d_out_off, L))) {
     kd_decoder_destroy(d);
     return rc;
@@ -443,6 +460,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->table);
   cudaFree(d->list);
   cudaFree(d->queue);
+  cudaFree(d->cand);
   cudaFree(d->d_items);
   cudaFree(d->d_counters);
   cudaFree(d->d_out_off);
@@ -571,7 +589,7 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
 
   kd::Params P = MakeParams(d);
   P.cols = cols;
-  P.row_in_smem = (static_cast<size_t>(cols) * sizeof(float) <= 32768) ? 1 : 0;
+  P.row_in_smem = (static_cast<size_t>(cols) * sizeof(double) <= 32768) ? 1 : 0;
 
   if (mem_kind == KD_MEM_DEVICE) {
     for (int32_t i = 0; i < m; ++i) {
@@ -842,6 +860,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->cycles_expand += L.cyc_expand;
     out->cycles_closure += L.cyc_closure;
     out->cycles_commit += L.cyc_commit;
+    out->slots_claimed += L.st_claimed;
   }
   return KD_OK;
 }

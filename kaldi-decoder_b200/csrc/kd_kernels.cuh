@@ -7,7 +7,7 @@
 //
 //   GetCutoff           faster-decoder.cc:244-336   -> lane_cutoff()
 //   ProcessEmitting     faster-decoder.cc:155-241   -> lane_expand_emitting()
-//   ProcessNonemitting  faster-decoder.cc:59-119    -> lane_closure()
+//   ProcessNonemitting  faster-decoder.cc:59-119    -> lane_closure_and_commit()
 //   token list / Token  faster-decoder.h:110-156,
 //                       hash-list-inl.h:127-173     -> per-lane open-addressing
 //                       table (key = state, 128-bit value = ordered fp64 cost |
@@ -26,6 +26,17 @@
 // {new_weight < C*}, independent of thread scheduling.  Equal-cost arrivals at
 // a state are resolved towards the lowest emitting-arc index (deterministic);
 // in the epsilon closure the incumbent stays (as in the reference).
+//
+// The search is latency bound, not bandwidth bound (profiles/r1_*): a lane-frame
+// is a chain of dependent L2 round trips executed by a handful of warps.  The
+// structure below is chosen to shorten that chain: the emitting arcs of a
+// whole tile of tokens are flattened (block prefix sum of out-degrees) so that
+// every thread keeps U independent 8-byte arc loads in flight; admitted arcs
+// (~3% of the visited ones) are parked in shared memory and recombined a
+// queue-full at a time; table operations start with a speculative CAS instead
+// of a load; the closure only visits states that have epsilon arcs (flag
+// carried in the arc record); the commit passes load four entries per thread
+// before using any.
 #ifndef KD_KERNELS_CUH_
 #define KD_KERNELS_CUH_
 
@@ -37,10 +48,10 @@ namespace kd {
 constexpr int kStatusHashOverflow = 1;
 constexpr int kStatusArenaOverflow = 2;
 constexpr int kStatusQueueOverflow = 4;
-constexpr int kStatusPathOverflow = 8;
 
+// In an arc field: "epsilon arc".  In a nextstate field: "state has epsilon arcs".
 constexpr uint32_t kEpsFlag = 0x80000000u;
-constexpr uint32_t kNoArc = 0x7FFFFFFFu;   // the start token's "arc"
+constexpr uint32_t kNoArc = 0x7FFFFFFFu;  // the start token's "arc"
 constexpr uint32_t kNoPrev = 0xFFFFFFFFu;
 constexpr int32_t kEmptyKey = -1;
 constexpr unsigned long long kEmptyCost = 0xFFFFFFFFFFFFFFFFull;
@@ -77,6 +88,7 @@ struct __align__(16) LaneState {
       st_tokens_out, st_max_tokens, st_sweeps;
   // SM cycles spent per phase (clock64 of thread 0), for the phase breakdown
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit;
+  long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
   // best-path selection results
   int32_t bp_ok, bp_final, bp_best_state;
   uint32_t bp_best_tok;    // arena index
@@ -94,10 +106,13 @@ struct AdvanceItem {
 };
 
 struct Params {
-  // graph (device)
+  // graph (device): CSR split into emitting and epsilon arcs.  The scan of the
+  // emitting arcs only needs (ilabel, weight): they are an 8-byte array of
+  // their own; (nextstate, olabel) are read for admitted arcs only.
   const int4 *st;      // [S]  {emit_begin, emit_count, eps_begin, eps_count}
-  const int4 *e_arc;   // [Ee] {ilabel, weight bits, nextstate, olabel}
-  const int4 *n_arc;   // [En] {olabel, weight bits, nextstate, 0}
+  const int2 *e_iw;    // [Ee] {ilabel, weight bits}
+  const int2 *e_no;    // [Ee] {nextstate | kEpsFlag if that state has eps arcs, olabel}
+  const int4 *n_arc;   // [En] {olabel, weight bits, nextstate | kEpsFlag ..., 0}
   const float *fin;    // [S]
   int32_t start;
   // options
@@ -118,7 +133,8 @@ struct Params {
   Entry *table;
   uint32_t *list;
   uint32_t *queue;  // 2 * qcap per lane
-  uint32_t hcap, hmask, lcap, qcap;
+  uint4 *cand;      // ccap per lane: arcs that passed the running-cutoff filter
+  uint32_t hcap, hmask, lcap, qcap, ccap;
   int32_t hshift;
   int32_t cols;
   int32_t row_in_smem;
@@ -146,6 +162,22 @@ __device__ __forceinline__ uint32_t fkey(float x) {
 __device__ __forceinline__ float funkey(uint32_t k) {
   uint32_t u = (k >> 31) ? (k & 0x7FFFFFFFu) : ~k;
   return __uint_as_float(u);
+}
+
+// Exact float -> double widening on the integer pipe.  The hardware conversion
+// (F2F.F64.F32) runs on the XU pipe, which two conversions per visited arc
+// saturate (ncu: sm__inst_executed_pipe_xu at its peak with 7 lanes per SM,
+// profiles/r1_v5_ncu_summary.txt); zero and normal numbers are rebuilt from
+// their bits instead, and only denormals, inf and NaN take the XU path.
+__device__ __forceinline__ double widen(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t mag = u & 0x7FFFFFFFu;
+  if (mag - 0x00800000u < 0x7F000000u) {  // normal: 0x00800000 <= mag < 0x7F800000
+    const uint32_t hi = (u & 0x80000000u) | ((mag >> 3) + (896u << 20));
+    return __hiloint2double(static_cast<int>(hi), static_cast<int>(u << 29));
+  }
+  if (mag == 0) return __hiloint2double(static_cast<int>(u), 0);  // +-0
+  return static_cast<double>(f);
 }
 
 __device__ __forceinline__ HVal ld_hval(const HVal *p) {
@@ -186,18 +218,19 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t *total) 
 }
 
 struct Shared {
-  double cstar;                // C* of the frame being processed
   double red_d[32];
   int red_i[32];
   uint32_t hist[256];
+  uint32_t warp_sums[32];
+  long long t_mark;
   uint32_t cut_fkey;  // running next-frame cutoff, rounded UP to float (a filter only)
   uint32_t acc_emit, acc_eps, acc_expanded;  // per-frame counters
   uint32_t list_n;
+  uint32_t cand_n;
   uint32_t q_n[2];
   uint32_t out_n;
-  uint32_t chunk;
+  uint32_t count;
   uint32_t sel_bin, sel_k;
-  long long t_mark;
   int status;
   int item;
 };
@@ -253,6 +286,7 @@ struct LaneBuf {
   Entry *table;
   uint32_t *list;
   uint32_t *queue;
+  uint4 *cand;
 };
 
 __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
@@ -264,13 +298,20 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   b.table = P.table + L * P.hcap;
   b.list = P.list + L * P.lcap;
   b.queue = P.queue + L * 2 * P.qcap;
+  b.cand = P.cand + L * P.ccap;
   return b;
 }
 
-// Finds the table slot of `state`, claiming an empty one if needed (then the
-// slot is appended to this frame's slot list).  Returns kNoIdx on overflow.
+// Finds the table slot of `state`, claiming an empty one if needed.  Probes are
+// plain loads; an atomic is spent only on an empty slot.  (Probing with the
+// CAS itself saves a round trip for new states but turns every arrival at an
+// existing state into an L2 atomic: measured slower, profiles/r1_v5_*.)  A
+// newly claimed slot is appended to this frame's slot list and, when
+// `eps_queue` is given (the state has epsilon arcs), to that queue: the
+// closure only visits those.  Returns kNoIdx on overflow.
 __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
-                                               int32_t state) {
+                                               int32_t state, uint32_t *eps_queue,
+                                               uint32_t *eps_queue_n) {
   // groups of 4 consecutive states share a 128-byte line; groups are scattered
   uint32_t h = ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
                (static_cast<uint32_t>(state) & 3u);
@@ -278,17 +319,25 @@ __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B
     int32_t k = __ldcg(&B.table[h].key);
     if (k == state) return h;
     if (k == kEmptyKey) {
-      int32_t old = atomicCAS(&B.table[h].key, kEmptyKey, state);
-      if (old == kEmptyKey) {
-        uint32_t pos = atomicAdd(&sh.list_n, 1u);
+      k = atomicCAS(&B.table[h].key, kEmptyKey, state);
+      if (k == state) return h;
+      if (k == kEmptyKey) {
+        const uint32_t pos = atomicAdd(&sh.list_n, 1u);
         if (pos < P.lcap) {
           B.list[pos] = h;
         } else {
           atomicOr(&sh.status, kStatusHashOverflow);
         }
+        if (eps_queue != nullptr) {
+          const uint32_t qp = atomicAdd(eps_queue_n, 1u);
+          if (qp < P.qcap) {
+            eps_queue[qp] = h;
+          } else {
+            atomicOr(&sh.status, kStatusQueueOverflow);
+          }
+        }
         return h;
       }
-      if (old == state) return h;
     }
     h = (h + 1) & P.hmask;
   }
@@ -297,6 +346,7 @@ __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B
 }
 
 // Emitting-phase recombination: keep the lexicographic minimum of (cost, arg).
+// Most arrivals at an occupied slot do not improve it: they cost one load.
 __device__ __forceinline__ void table_min(HVal *slot, HVal mine) {
   HVal cur = ld_hval(slot);
   while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
@@ -304,6 +354,23 @@ __device__ __forceinline__ void table_min(HVal *slot, HVal mine) {
     if (got.cost == cur.cost && got.arg == cur.arg) return;
     cur = got;
   }
+}
+
+// Block-wide count of tokens with float(cost) <= bound (used to skip the exact
+// order statistic when min_active cannot bind).
+template <int THREADS>
+__device__ uint32_t block_count_le(const double *cost, int n, double bound, Shared &sh) {
+  if (threadIdx.x == 0) sh.count = 0;
+  __syncthreads();
+  uint32_t c = 0;
+  for (int i = threadIdx.x; i < n; i += THREADS)
+    c += (static_cast<double>(static_cast<float>(cost[i])) <= bound) ? 1u : 0u;
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh.count, c);
+  __syncthreads();
+  const uint32_t r = sh.count;
+  __syncthreads();
+  return r;
 }
 
 // GetCutoff's order statistic: the k-th smallest (0-based) of float(cost[i]).
@@ -370,10 +437,19 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, double b
     return;
   }
   if (n > P.min_active) {
-    if (P.min_active == 0)
+    if (P.min_active == 0) {
       min_cut = best;
-    else
-      min_cut = static_cast<double>(select_kth<THREADS>(cost, n, P.min_active, sh));
+    } else {
+      // The (min_active+1)-th smallest exceeds beam_cutoff iff at most
+      // min_active values are <= beam_cutoff: one counting pass decides
+      // whether the exact order statistic is needed at all.
+      const uint32_t c = block_count_le<THREADS>(cost, n, beam_cutoff, sh);
+      if (c > static_cast<uint32_t>(P.min_active)) {
+        min_cut = beam_cutoff;  // some value <= beam_cutoff: min_active does not bind
+      } else {
+        min_cut = static_cast<double>(select_kth<THREADS>(cost, n, P.min_active, sh));
+      }
+    }
   }
   if (min_cut > beam_cutoff) {
     *adaptive_beam = static_cast<float>(min_cut - best + static_cast<double>(P.beam_delta));
@@ -388,58 +464,67 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, double b
 // cutoff (done by the caller), inserted if the state is new, replaces the
 // incumbent only if strictly better.  An incumbent left over from the emitting
 // phase with cost >= C* is not a token (see file comment) and is overwritten.
+// A token that was created or improved is queued for expansion when its state
+// has epsilon arcs (flag in the arc's nextstate word).
 __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
-                                            int32_t dst, unsigned long long cost_key,
+                                            uint32_t dst_word, unsigned long long cost_key,
                                             uint32_t arc, uint32_t src_slot,
                                             unsigned long long cstar_key, uint32_t *q_next,
                                             uint32_t *q_next_n) {
-  uint32_t h = table_slot(P, B, sh, dst);
+  const uint32_t h =
+      table_slot(P, B, sh, static_cast<int32_t>(dst_word & ~kEpsFlag), nullptr, nullptr);
   if (h == kNoIdx) return;
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_slot;
   HVal cur = ld_hval(&B.table[h].val);
   while (true) {
-    bool cur_is_eps = (cur.arg >> 63) != 0;
-    bool replace = mine.cost < cur.cost || (!cur_is_eps && !(cur.cost < cstar_key));
+    const bool cur_is_eps = (cur.arg >> 63) != 0;
+    const bool replace = mine.cost < cur.cost || (!cur_is_eps && !(cur.cost < cstar_key));
     if (!replace) return;
     HVal got = cas_hval(&B.table[h].val, cur, mine);
     if (got.cost == cur.cost && got.arg == cur.arg) break;
     cur = got;
   }
-  uint32_t pos = atomicAdd(q_next_n, 1u);
-  if (pos < P.qcap) {
-    q_next[pos] = h;
-  } else {
-    atomicOr(&sh.status, kStatusQueueOverflow);
+  if (dst_word & kEpsFlag) {
+    const uint32_t pos = atomicAdd(q_next_n, 1u);
+    if (pos < P.qcap) {
+      q_next[pos] = h;
+    } else {
+      atomicOr(&sh.status, kStatusQueueOverflow);
+    }
   }
 }
 
+// Expands the epsilon arcs of the token in table slot `slot`
+// (faster-decoder.cc:71-117).
 __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Shared &sh,
                                            uint32_t slot, unsigned long long cstar_key,
                                            double cstar, uint32_t *q_next, uint32_t *q_next_n,
                                            uint32_t *eps_count) {
-  HVal v = ld_hval(&B.table[slot].val);
-  bool is_eps = (v.arg >> 63) != 0;
+  const HVal v = ld_hval(&B.table[slot].val);
+  const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(v.cost < cstar_key || is_eps)) return;
-  int32_t state = __ldcg(&B.table[slot].key);
-  int4 st = __ldg(P.st + state);
+  const int32_t state = __ldcg(&B.table[slot].key);
+  const int4 st = __ldg(P.st + state);
   if (st.w == 0) return;
-  double cost = dunkey(v.cost);
+  const double cost = dunkey(v.cost);
   *eps_count += static_cast<uint32_t>(st.w);
   for (int a = st.z; a < st.z + st.w; ++a) {
-    int4 arc = __ldg(P.n_arc + a);
-    double nc = cost + static_cast<double>(__int_as_float(arc.y));
+    const int4 arc = __ldg(P.n_arc + a);
+    const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
-    eps_arrival(P, B, sh, arc.z, dkey(nc), static_cast<uint32_t>(a), slot, cstar_key, q_next,
-                q_next_n);
+    eps_arrival(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a), slot,
+                cstar_key, q_next, q_next_n);
   }
 }
 
 // Epsilon closure (faster-decoder.cc:59-119) followed by the commit of the
 // frame: live table entries become the next token block in the arena, the
 // table is wiped, and the block's min cost is recorded for the next GetCutoff.
+// On entry queue 0 holds the slots, claimed during the emitting phase (or by
+// InitDecoding), whose states have epsilon arcs.
 template <int THREADS>
 __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
                                         LaneState &ls, double cstar) {
@@ -447,25 +532,19 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   const unsigned long long cstar_key = dkey(cstar);
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const long long t_begin = clock64();
-  // ---- closure: sweep 0 expands every token, later sweeps the improved ones
   if (tid == 0) {
-    sh.q_n[0] = 0;
     sh.q_n[1] = 0;
     sh.out_n = 0;
     sh.acc_eps = 0;
   }
   __syncthreads();
+  // ---- closure: sweep 0 expands the candidates, later sweeps the improved ones
   uint32_t eps_count = 0;
-  const uint32_t m0 = min(sh.list_n, P.lcap);
-  __syncthreads();  // everyone holds m0 before the closure starts growing the list
   uint32_t *q0 = B.queue, *q1 = B.queue + P.qcap;
-  for (uint32_t p = tid; p < m0; p += THREADS)
-    expand_eps(P, B, sh, B.list[p], cstar_key, cstar, q0, &sh.q_n[0], &eps_count);
-  __syncthreads();
   int cur = 0;
-  long long sweeps = 1;
+  long long sweeps = 0;
   while (true) {
-    uint32_t qn = min(sh.q_n[cur], P.qcap);
+    const uint32_t qn = min(sh.q_n[cur], P.qcap);
     if (qn == 0 || sh.status != 0) break;
     __syncthreads();
     if (tid == 0) sh.q_n[cur ^ 1] = 0;
@@ -479,26 +558,34 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   }
   __syncthreads();
   const long long t_mid = clock64();
-  // ---- commit, pass 1: number the live entries
+  // ---- commit, pass 1: number the live entries (4 entries per thread in flight)
   const uint32_t m = min(sh.list_n, P.lcap);
-  for (uint32_t p0 = 0; p0 < m; p0 += THREADS) {  // uniform trip count: full-warp ballots
-    const uint32_t p = p0 + tid;
-    uint32_t h = 0;
-    bool live = false;
-    if (p < m) {
-      h = B.list[p];
-      HVal v = ld_hval(&B.table[h].val);
-      live = v.cost != kEmptyCost && (v.cost < cstar_key || (v.arg >> 63) != 0);
+  for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {  // uniform trip count: full-warp ballots
+    uint32_t h[4];
+    HVal v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t p = p0 + u * THREADS + tid;
+      h[u] = p < m ? B.list[p] : kNoIdx;
     }
-    // warp-aggregated numbering: one shared-memory atomic per warp
-    const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, live);
-    uint32_t wbase = 0;
-    if ((tid & 31) == 0 && live_mask) wbase = atomicAdd(&sh.out_n, __popc(live_mask));
-    wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-    if (p < m) {
-      uint32_t idx = kNoIdx;
-      if (live) idx = wbase + __popc(live_mask & ((1u << (tid & 31)) - 1u));
-      B.table[h].idx = idx;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].cost = kEmptyCost;
+      v[u].arg = kEmptyArg;
+      if (h[u] != kNoIdx) v[u] = ld_hval(&B.table[h[u]].val);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool live =
+          v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
+      // warp-aggregated numbering: one shared-memory atomic per warp
+      const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, live);
+      uint32_t wbase = 0;
+      if ((tid & 31) == 0 && live_mask) wbase = atomicAdd(&sh.out_n, __popc(live_mask));
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+      if (h[u] != kNoIdx)
+        B.table[h[u]].idx =
+            live ? wbase + __popc(live_mask & ((1u << (tid & 31)) - 1u)) : kNoIdx;
     }
   }
   __syncthreads();
@@ -509,35 +596,60 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   }
   __syncthreads();
   const bool write_ok = (sh.status & kStatusArenaOverflow) == 0;
-  // ---- commit, pass 2: write records, wipe the table
+  // ---- commit, pass 2: write the token block and wipe the table.  A thread
+  // wipes (key, val) of its own entries after reading them; other threads
+  // read nothing but `idx` of foreign entries, which is never wiped.
   double my_min = inf;
   int my_arg = -1;
-  for (uint32_t p = tid; p < m; p += THREADS) {
-    uint32_t h = B.list[p];
-    uint32_t idx = B.table[h].idx;
-    if (idx != kNoIdx && write_ok) {
-      HVal v = ld_hval(&B.table[h].val);
-      uint32_t arc = static_cast<uint32_t>(v.arg >> 32);
-      uint32_t prev = static_cast<uint32_t>(v.arg);
-      if (arc & kEpsFlag) prev = new_base + B.table[prev].idx;
-      double c = dunkey(v.cost);
-      B.a_cost[new_base + idx] = c;
-      B.a_link[new_base + idx] = (static_cast<unsigned long long>(arc) << 32) | prev;
-      B.a_state[new_base + idx] = __ldcg(&B.table[h].key);
-      if (c < my_min) {
-        my_min = c;
-        my_arg = static_cast<int>(idx);
+  for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {
+    uint32_t h[4];
+    HVal v[4];
+    int4 meta[4];  // {key, idx, pad, pad}
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t p = p0 + u * THREADS + tid;
+      h[u] = p < m ? B.list[p] : kNoIdx;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u].cost = kEmptyCost;
+      v[u].arg = kEmptyArg;
+      meta[u] = make_int4(kEmptyKey, static_cast<int>(kNoIdx), 0, 0);
+      if (h[u] != kNoIdx) {
+        v[u] = ld_hval(&B.table[h[u]].val);
+        meta[u] = __ldcg(reinterpret_cast<const int4 *>(&B.table[h[u]].key));
       }
     }
-  }
-  __syncthreads();  // every idx/key read above precedes the wipe below
-  for (uint32_t p = tid; p < m; p += THREADS) {
-    uint32_t h = B.list[p];
-    ulonglong2 e;
-    e.x = kEmptyCost;
-    e.y = kEmptyArg;
-    *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = e;
-    B.table[h].key = kEmptyKey;
+    uint32_t prev_idx[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      prev_idx[u] = 0;
+      if (h[u] != kNoIdx && static_cast<uint32_t>(meta[u].y) != kNoIdx && (v[u].arg >> 63) != 0)
+        prev_idx[u] = __ldcg(&B.table[static_cast<uint32_t>(v[u].arg)].idx);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (h[u] == kNoIdx) continue;
+      const uint32_t idx = static_cast<uint32_t>(meta[u].y);
+      if (idx != kNoIdx && write_ok) {
+        const uint32_t arc = static_cast<uint32_t>(v[u].arg >> 32);
+        uint32_t prev = static_cast<uint32_t>(v[u].arg);
+        if (arc & kEpsFlag) prev = new_base + prev_idx[u];
+        const double c = dunkey(v[u].cost);
+        B.a_cost[new_base + idx] = c;
+        B.a_link[new_base + idx] = (static_cast<unsigned long long>(arc) << 32) | prev;
+        B.a_state[new_base + idx] = meta[u].x;
+        if (c < my_min) {
+          my_min = c;
+          my_arg = static_cast<int>(idx);
+        }
+      }
+      ulonglong2 e;
+      e.x = kEmptyCost;
+      e.y = kEmptyArg;
+      *reinterpret_cast<ulonglong2 *>(&B.table[h[u]].val) = e;
+      B.table[h[u]].key = kEmptyKey;
+    }
   }
   double bmin;
   int barg;
@@ -559,133 +671,90 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.best_idx = -1;
     }
     ls.st_sweeps += sweeps;
+    ls.st_claimed += m;
     ls.st_eps_arcs += sh.acc_eps;
     ls.cyc_closure += t_mid - t_begin;
     ls.cyc_commit += clock64() - t_mid;
     sh.list_n = 0;
+    sh.q_n[0] = 0;
   }
   __syncthreads();
 }
 
-// Admitted emitting arcs are not recombined where they are found: ~97% of the
-// arcs a frame visits fail the pruning test, so a warp iteration over 32 arcs
-// admits about one, and recombining it in place makes 31 lanes wait for one
-// lane's table round trips (profiles/r1_v1_ncu_summary.txt).  Instead each
-// warp parks admitted arcs in a shared-memory queue (one native 32-bit
-// shared-memory atomicAdd per admitted arc, nothing per rejected arc) and
-// recombines 32 of them at a time, one per lane, so the table latencies overlap.
-constexpr uint32_t kQueueCap = 192;  // 31 left over + at most 4 x 32 parked between checks
-
-struct WarpQueue {
-  unsigned long long nk[kQueueCap];   // ordered fp64 cost
-  unsigned long long arg[kQueueCap];  // (arc << 32) | source token
-  int32_t dst[kQueueCap];             // destination state
-  uint32_t n;
-  uint32_t pad[3];
-};
-
-__device__ __forceinline__ void queue_insert_one(const Params &P, const LaneBuf &B, Shared &sh,
-                                                 const WarpQueue &q, uint32_t e) {
-  const unsigned long long nk = q.nk[e];
-  // the running cutoff may have tightened since the arc was parked
-  const double cut_now =
-      static_cast<double>(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
-  if (!(dunkey(nk) < cut_now)) return;
-  uint32_t h = table_slot(P, B, sh, q.dst[e]);
+// Recombines one emitting arc that survived pruning at its destination state.
+__device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
+                                           uint32_t a, unsigned long long nk, uint32_t tok_abs) {
+  const int2 no = __ldg(P.e_no + a);
+  const bool has_eps = no.x < 0;
+  const uint32_t h = table_slot(P, B, sh, no.x & 0x7FFFFFFF, has_eps ? B.queue : nullptr,
+                                &sh.q_n[0]);
   if (h == kNoIdx) return;
   HVal mine;
   mine.cost = nk;
-  mine.arg = q.arg[e];
+  mine.arg = (static_cast<unsigned long long>(a) << 32) | tok_abs;
   table_min(&B.table[h].val, mine);
 }
 
-// Warp-convergent: recombines full groups of 32 parked arcs.
-__device__ __forceinline__ void queue_drain_full(const Params &P, const LaneBuf &B, Shared &sh,
-                                                 WarpQueue &q) {
-  uint32_t n = *reinterpret_cast<volatile uint32_t *>(&q.n);
-  if (n < 32) return;  // q.n is only written by this warp: the value is warp-uniform
-  __syncwarp();
-  do {
-    queue_insert_one(P, B, sh, q, n - 32 + (threadIdx.x & 31));
-    n -= 32;
-  } while (n >= 32);
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) q.n = n;
-  __syncwarp();
-}
-
-// Four emitting arcs per thread (faster-decoder.cc:208-229): new_weight =
-// (w + cost) + ac for all four first -- straight-line code the compiler can
-// interleave -- then the rare admitted ones are parked.  The shared running
-// cutoff is kept as a float rounded UP (one native 32-bit shared-memory
-// atomicMin); it only filters.  The exact C* comes from the per-thread fp64
-// minimum `my_min` reduced at the end of the frame: the arc with the globally
-// smallest new_weight always passes the filter.  Slots with bit u of `vmask`
-// clear hold a dummy arc (ilabel 1) and are ignored.
-template <bool ROW_SMEM>
-__device__ __forceinline__ void emit4(Shared &sh, WarpQueue &q, const float *row,
-                                      const int4 (&ar)[4], uint32_t vmask, uint32_t a0,
-                                      uint32_t a_stride, double tcost, uint32_t tok_abs,
-                                      double ab, double &my_min) {
-  const double cut_d =
-      static_cast<double>(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
-  double nw[4];
-  uint32_t adm = 0;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const float lp = ROW_SMEM ? row[ar[u].x - 1] : __ldg(row + ar[u].x - 1);
-    nw[u] = (static_cast<double>(__int_as_float(ar[u].y)) + tcost) + static_cast<double>(-lp);
-    if (nw[u] < cut_d) adm |= 1u << u;  // faster-decoder.cc:211 (filter; exact test at commit)
-  }
-  adm &= vmask;
-  if (adm == 0) return;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    if (adm & (1u << u)) {
-      const uint32_t e = atomicAdd(&q.n, 1u);
-      q.nk[e] = dkey(nw[u]);
-      q.arg[e] = (static_cast<unsigned long long>(a0 + a_stride * u) << 32) | tok_abs;
-      q.dst[e] = ar[u].z;
-      if (nw[u] < my_min) {
-        my_min = nw[u];
-        const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));  // faster-decoder.cc:215-217
-        if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)) atomicMin(&sh.cut_fkey, fk);
-      }
-    }
-  }
-}
+constexpr int kWindows = 4;  // 32-arc windows a warp keeps in flight
 
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
 //
-// Work mapping: a warp takes 32 tokens at a time.  Tokens with few emitting
-// arcs (<= kSmallDeg, the bulk of a lexicon trie) are expanded by their own
-// thread; tokens with many arcs (trie roots, H states) are expanded by the
-// whole warp, 32 consecutive 16-byte arcs per load instruction.
-constexpr uint32_t kSmallDeg = 8;
-
+// Three steps: scan -> exact cutoff -> recombine.
+//
+// Scan.  The tokens are taken a tile (4 per thread) at a time.  Tokens that
+// will be expanded (cost < weight_cutoff, at least one emitting arc) are
+// compacted into shared memory together with the exclusive prefix sum of their
+// emitting out-degrees, so the tile's arcs form one flat index space.  Each
+// warp owns a contiguous slice of it and walks it 32 arcs (one coalesced
+// window) at a time, kWindows windows in flight.  The token owning each arc of
+// a window comes from a bit mask of the token boundaries falling inside the
+// window (one shared-memory load, one warp OR-reduction, one popc).
+// new_weight = (w + cost) + ac is computed for all arcs of a step first
+// (straight-line code).  ~97% of the arcs fail the pruning test and cost
+// nothing more.  The others are only *candidates*: the test is made against a
+// running cutoff (the reference's next_weight_cutoff, faster-decoder.cc:172-217)
+// kept in shared memory as a float rounded UP and lowered with one native
+// 32-bit atomicMin; it is looser than the final cutoff.  Candidates are
+// appended to a per-lane buffer, not recombined: recombining them on the spot
+// makes a warp wait for one lane's table round trips, and fills the table
+// (and L2) with arrivals that the final cutoff rejects -- 3x more slots claimed
+// than tokens kept (profiles/r1_v5_ncu_summary.txt).
+//
+// Exact cutoff.  C* = min(new_weight) + adaptive_beam (faster-decoder.cc:240)
+// from the per-thread fp64 minima: the arc with the globally smallest
+// new_weight always passes the filter, so the minimum over candidates is the
+// minimum over all arcs.
+//
+// Recombine.  All threads walk the candidate buffer; only candidates with
+// new_weight < C* touch the table, so the table holds exactly the tokens.
 template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       LaneState &ls, const float *row_g, float *s_row,
-                                       WarpQueue *queues) {
-  const int tid = threadIdx.x, lane = tid & 31;
+                                       LaneState &ls, const float *row_g, double *s_row,
+                                       double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
+                                       uint16_t *t_tok) {
+  constexpr int U = kWindows;
+  constexpr int TT = THREADS * 4;
+  constexpr int NW = THREADS / 32;
+  constexpr int kSearchStep = TT > 2048 ? 2048 : TT > 1024 ? 1024 : TT > 512 ? 512 : 256;
+  static_assert(TT <= 4096 && TT > 256 && NW <= 16, "tile size out of range");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const int n = ls.n_tok;
   const uint32_t base = ls.tok_base;
   const double *cost = B.a_cost + base;
   const int32_t *state = B.a_state + base;
-  WarpQueue &q = queues[tid >> 5];
   const long long t_begin = clock64();
 
-  // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29)
-  const float *row = row_g;
+  // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29),
+  // already negated (faster-decoder.cc:209) and widened to fp64
   if (ROW_SMEM) {
-    for (int i = tid; i < P.cols; i += THREADS) s_row[i] = __ldg(row_g + i);
-    row = s_row;
+    for (int i = tid; i < P.cols; i += THREADS)
+      s_row[i] = static_cast<double>(-__ldg(row_g + i));
   }
   if (tid == 0) {
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
-    sh.chunk = 0;
     sh.acc_emit = sh.acc_expanded = 0;
+    sh.cand_n = 0;
   }
   double wc;
   float abf;
@@ -696,12 +765,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189)
   double seed = inf;
   if (n > 0 && ls.best_cost < wc) {
-    int4 st = __ldg(P.st + state[ls.best_idx]);
+    const int4 st = __ldg(P.st + state[ls.best_idx]);
     for (int a = tid; a < st.y; a += THREADS) {
-      int4 arc = __ldg(P.e_arc + st.x + a);
-      const float lp = ROW_SMEM ? row[arc.x - 1] : __ldg(row + arc.x - 1);
-      double nw = (static_cast<double>(__int_as_float(arc.y)) + ls.best_cost) +
-                  static_cast<double>(-lp);
+      const int2 iw = __ldg(P.e_iw + st.x + a);
+      const double ac = ROW_SMEM ? s_row[iw.x - 1] : widen(-__ldg(row_g + iw.x - 1));
+      const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
       seed = fmin(seed, nw);
     }
   }
@@ -714,105 +782,196 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   }
   if (tid == 0) sh.t_mark = clock64();
 
+  // ---------------------------------------------------------------- scan
   uint32_t n_expanded = 0, n_arcs = 0;
   double my_min = inf;
-  if (lane == 0) q.n = 0;
-  __syncwarp();
-  while (true) {
-    uint32_t c = 0;
-    if (lane == 0) c = atomicAdd(&sh.chunk, 1u);
-    c = __shfl_sync(0xFFFFFFFFu, c, 0);
-    const uint32_t i0 = c * 32u;
-    if (i0 >= static_cast<uint32_t>(n)) break;
-    const uint32_t i = i0 + lane;
-    double tc = inf;
-    uint32_t cnt = 0, beg = 0;
-    if (i < static_cast<uint32_t>(n)) {
-      tc = cost[i];
-      if (tc < wc) {  // faster-decoder.cc:202
-        int4 st = __ldg(P.st + state[i]);
-        beg = static_cast<uint32_t>(st.x);
-        cnt = static_cast<uint32_t>(st.y);
-        ++n_expanded;
-        n_arcs += cnt;
-      }
-    }
-    const bool big = cnt > kSmallDeg;
-    // (i) small tokens: each thread walks its own arcs, 4 at a time
-    const uint32_t scnt = big ? 0u : cnt;
-#pragma unroll 1
-    for (uint32_t k0 = 0; k0 < kSmallDeg; k0 += 4) {
-      if (!__any_sync(0xFFFFFFFFu, k0 < scnt)) break;
-      int4 ar[4];
-      uint32_t vmask = 0;
+  for (uint32_t tile0 = 0; tile0 < static_cast<uint32_t>(n); tile0 += TT) {
+    // tile setup: 4 consecutive tokens per thread -> compacted (cost, arc
+    // range, arc prefix) of the tokens to expand
+    uint32_t cnt[4], beg[4];
+    double tc[4];
+    {
+      int32_t ts[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        ar[u] = make_int4(1, 0, 0, 0);
-        if (k0 + u < scnt) {
-          ar[u] = __ldg(P.e_arc + beg + k0 + u);
-          vmask |= 1u << u;
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t i = tile0 + 4 * tid + k;
+        tc[k] = inf;
+        ts[k] = -1;
+        if (i < static_cast<uint32_t>(n)) {
+          tc[k] = cost[i];
+          ts[k] = state[i];
         }
       }
-      emit4<ROW_SMEM>(sh, q, row, ar, vmask, beg + k0, 1u, tc, base + i, ab, my_min);
-      queue_drain_full(P, B, sh, q);
-    }
-    // (ii) big tokens: the warp walks the arc range together, 4 x 32 arcs per step
-    uint32_t bm = __ballot_sync(0xFFFFFFFFu, big);
-    while (bm) {
-      const int src = __ffs(bm) - 1;
-      bm &= bm - 1;
-      const uint32_t b = __shfl_sync(0xFFFFFFFFu, beg, src);
-      const uint32_t cn = __shfl_sync(0xFFFFFFFFu, cnt, src);
-      const double cst = __shfl_sync(0xFFFFFFFFu, tc, src);
-      const uint32_t tok_abs = base + i0 + src;
-#pragma unroll 1
-      for (uint32_t j0 = 0; j0 < cn; j0 += 128) {
-        int4 ar[4];
-        uint32_t vmask = 0;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t j = j0 + 32u * u + lane;
-          ar[u] = make_int4(1, 0, 0, 0);
-          if (j < cn) {
-            ar[u] = __ldg(P.e_arc + b + j);
-            vmask |= 1u << u;
+      for (int k = 0; k < 4; ++k) {
+        cnt[k] = 0;
+        beg[k] = 0;
+        if (ts[k] >= 0 && tc[k] < wc) {  // faster-decoder.cc:202
+          const int4 st = __ldg(P.st + ts[k]);
+          beg[k] = static_cast<uint32_t>(st.x);
+          cnt[k] = static_cast<uint32_t>(st.y);
+          ++n_expanded;
+          n_arcs += cnt[k];
+        }
+      }
+    }
+    const uint32_t my_arcs = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+    const uint32_t my_toks = (cnt[0] != 0) + (cnt[1] != 0) + (cnt[2] != 0) + (cnt[3] != 0);
+    uint32_t w_arcs, w_toks;
+    uint32_t ex_arcs = warp_excl_scan(my_arcs, &w_arcs);
+    uint32_t ex_toks = warp_excl_scan(my_toks, &w_toks);
+    if (lane == 0) {
+      sh.warp_sums[warp] = w_arcs;
+      sh.warp_sums[16 + warp] = w_toks;
+    }
+    __syncthreads();
+    uint32_t n_flat = 0, n_comp = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t a = sh.warp_sums[w], t = sh.warp_sums[16 + w];
+      if (w < warp) {
+        ex_arcs += a;
+        ex_toks += t;
+      }
+      n_flat += a;
+      n_comp += t;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (cnt[k] != 0) {
+        t_ex[ex_toks] = ex_arcs;
+        t_beg[ex_toks] = beg[k];
+        t_cost[ex_toks] = tc[k];
+        t_tok[ex_toks] = static_cast<uint16_t>(4 * tid + k);
+        ex_arcs += cnt[k];
+        ++ex_toks;
+      }
+    }
+    if (tid == 0) t_ex[n_comp] = n_flat;
+    __syncthreads();
+    // flat arc loop: this warp's slice is [jw0, jw1)
+    const uint32_t per_warp = ((n_flat + NW * 32 - 1) / (NW * 32)) * 32;
+    const uint32_t jw0 = warp * per_warp;
+    const uint32_t jw1 = min(n_flat, jw0 + per_warp);
+    if (jw0 < jw1) {
+      uint32_t t_lo = 0;  // compacted token owning arc jw0: largest t with t_ex[t] <= jw0
+#pragma unroll
+      for (int s = kSearchStep; s; s >>= 1)
+        if (t_lo + s < n_comp && t_ex[t_lo + s] <= jw0) t_lo += s;
+#pragma unroll 1
+      for (uint32_t jb = jw0; jb < jw1; jb += 32 * U) {
+        int2 iw[U];
+        uint32_t tt[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t j0 = jb + 32 * u;
+          const uint32_t j = j0 + lane;
+          iw[u] = make_int2(1, 0);
+          tt[u] = kNoIdx;
+          if (j0 < jw1) {  // warp-uniform
+            // boundaries (first arc index) of the 32 tokens after t_lo
+            const uint32_t bnd = t_ex[min(t_lo + 1 + lane, n_comp)];
+            const uint32_t p = bnd - j0;  // >= 1: token t_lo owns arc j0
+            const uint32_t mask = __reduce_or_sync(0xFFFFFFFFu, p < 32 ? (1u << p) : 0u);
+            const bool edge = __any_sync(0xFFFFFFFFu, p == 32);
+            const uint32_t t = t_lo + __popc(mask & ((2u << lane) - 1u));
+            if (j < jw1) {
+              tt[u] = t;
+              iw[u] = __ldg(P.e_iw + t_beg[t] + (j - t_ex[t]));
+            }
+            t_lo += __popc(mask) + (edge ? 1u : 0u);
           }
         }
-        emit4<ROW_SMEM>(sh, q, row, ar, vmask, b + j0 + lane, 32u, cst, tok_abs, ab, my_min);
-        queue_drain_full(P, B, sh, q);
+        const double cut_d = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
+        double nw[U];
+        uint32_t adm = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const double ac = ROW_SMEM ? s_row[iw[u].x - 1] : widen(-__ldg(row_g + iw[u].x - 1));
+          const double tcst = t_cost[min(tt[u], static_cast<uint32_t>(TT - 1))];
+          nw[u] = (widen(__int_as_float(iw[u].y)) + tcst) + ac;
+          // faster-decoder.cc:211 against the running cutoff
+          if (tt[u] != kNoIdx && nw[u] < cut_d) adm |= 1u << u;
+        }
+        if (adm) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (adm & (1u << u)) {
+              const uint32_t j = jb + 32 * u + lane;
+              const uint32_t t = tt[u];
+              const uint32_t a = t_beg[t] + (j - t_ex[t]);
+              const uint32_t tok_abs = base + tile0 + t_tok[t];
+              const unsigned long long nk = dkey(nw[u]);
+              const uint32_t e = atomicAdd(&sh.cand_n, 1u);
+              if (e < P.ccap) {
+                B.cand[e] = make_uint4(static_cast<uint32_t>(nk), static_cast<uint32_t>(nk >> 32),
+                                       a, tok_abs);
+              } else {
+                insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
+              }
+              if (nw[u] < my_min) {
+                my_min = nw[u];
+                // faster-decoder.cc:215-217
+                const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));
+                if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
+                  atomicMin(&sh.cut_fkey, fk);
+              }
+            }
+          }
+        }
       }
     }
+    __syncthreads();  // the tile arrays are rewritten by the next tile
   }
-  // recombine what is still parked
-  __syncwarp();
-  if (lane < *reinterpret_cast<volatile uint32_t *>(&q.n)) queue_insert_one(P, B, sh, q, lane);
   n_expanded = __reduce_add_sync(0xFFFFFFFFu, n_expanded);
   n_arcs = __reduce_add_sync(0xFFFFFFFFu, n_arcs);
   if (lane == 0 && n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
   if (lane == 0 && n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
-  // exact C* = min(new_weight) + adaptive_beam (faster-decoder.cc:240), including the seed
+  // ---------------------------------------------------------------- exact cutoff
   double bmin;
   int dummy2;
   block_min_arg<THREADS>(fmin(my_min, seed), 0, sh, &bmin, &dummy2);
+  const double cstar = bmin + ab;
+  const unsigned long long cstar_key = dkey(cstar);
+  // ---------------------------------------------------------------- recombine
+  const uint32_t n_cand = min(sh.cand_n, P.ccap);
+  for (uint32_t e = tid; e < n_cand; e += THREADS) {
+    const uint4 c = __ldcg(B.cand + e);
+    const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
+    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);
+  }
+  __syncthreads();
   if (tid == 0) {
     const long long t_end = clock64();
     ls.cyc_cutoff += sh.t_mark - t_begin;
     ls.cyc_expand += t_end - sh.t_mark;
   }
-  return bmin + ab;
+  return cstar;
 }
 
 // ------------------------------------------------------------------ kernels
 
+// Dynamic shared memory of kd_advance_kernel without the log-prob row, bytes.
+template <int THREADS>
+__host__ __device__ constexpr size_t advance_smem_fixed() {
+  return THREADS * 4 * (sizeof(double) + 4) +  // t_cost, t_beg
+         (THREADS * 4 + 4) * 4 +               // t_ex
+         THREADS * 4 * 2;                      // t_tok
+}
+
 template <int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
+  constexpr int TT = THREADS * 4;
   __shared__ Shared sh;
   __shared__ LaneState ls;
   __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
   const LaneBuf &B = sB;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  WarpQueue *queues = reinterpret_cast<WarpQueue *>(dyn_smem);
-  float *s_row = reinterpret_cast<float *>(dyn_smem + (THREADS / 32) * sizeof(WarpQueue));
+  double *t_cost = reinterpret_cast<double *>(dyn_smem);
+  uint32_t *t_beg = reinterpret_cast<uint32_t *>(t_cost + TT);
+  uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
+  uint16_t *t_tok = reinterpret_cast<uint16_t *>(t_ex + TT + 4);
+  double *s_row = reinterpret_cast<double *>(t_tok + TT);  // TT * 2 bytes: 8-byte aligned
   const int tid = threadIdx.x;
 
   while (true) {
@@ -826,6 +985,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       ls = P.lanes[it.lane];
       sh.status = ls.status;
       sh.list_n = 0;
+      sh.q_n[0] = 0;
     }
     __syncthreads();
     while (ls.frames_decoded < it.target && sh.status == 0) {
@@ -834,9 +994,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       const int n_in = ls.n_tok;
       double cstar;
       if (P.row_in_smem)
-        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row, queues);
+        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
+                                                    t_beg, t_tok);
       else
-        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, queues);
+        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
+                                                     t_beg, t_tok);
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar);
       if (tid == 0) {
         ls.frames_decoded = frame + 1;
@@ -877,10 +1039,13 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     ls = z;
     sh.status = 0;
     sh.list_n = 0;
+    sh.q_n[0] = 0;
   }
   __syncthreads();
   if (tid == 0) {
-    uint32_t h = table_slot(P, B, sh, P.start);
+    const int4 st = __ldg(P.st + P.start);
+    const uint32_t h =
+        table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
     HVal v;
     v.cost = dkey(0.0);
     v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
@@ -893,6 +1058,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     ls.st_sweeps = 0;
     ls.st_eps_arcs = 0;
     ls.cyc_closure = ls.cyc_commit = 0;
+    ls.st_claimed = 0;
     P.lanes[lane] = ls;
   }
 }
@@ -903,6 +1069,7 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
   __shared__ Shared sh;
   __shared__ int s_any_final;
+  __shared__ uint32_t s_best_tok;
   const int tid = threadIdx.x;
   const int lane = P.items[blockIdx.x].lane;
   const LaneBuf B = lane_buffers(P, lane);
@@ -910,7 +1077,10 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
   const int n = L->n_tok;
   const uint32_t base = L->tok_base;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
-  if (tid == 0) s_any_final = 0;
+  if (tid == 0) {
+    s_any_final = 0;
+    s_best_tok = kNoIdx;
+  }
   __syncthreads();
   int any = 0;
   for (int i = tid; i < n; i += THREADS) {
@@ -936,11 +1106,6 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
   int rs;
   // block_min_arg treats idx -1 as "none" (largest unsigned)
   block_min_arg<THREADS>(bs < 0 ? inf : bv, bs, sh, &rv, &rs);
-  // a token with cost +inf and no competitor: the reduction cannot tell it
-  // from "none"; such tokens never exist (arrivals need cost < cutoff).
-  __shared__ uint32_t s_best_tok;
-  if (tid == 0) s_best_tok = kNoIdx;
-  __syncthreads();
   if (rs >= 0) {
     for (int i = tid; i < n; i += THREADS)
       if (B.a_state[base + i] == rs) s_best_tok = base + i;
@@ -993,19 +1158,21 @@ __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t 
     if (arc == kNoArc) break;
     uint32_t prev = static_cast<uint32_t>(link);
     double pc = B.a_cost[prev];
-    int4 a;
     int32_t ilab, olab;
+    float graph;
     if (arc & kEpsFlag) {
-      a = __ldg(P.n_arc + (arc & ~kEpsFlag));
+      const int4 a = __ldg(P.n_arc + (arc & ~kEpsFlag));
       ilab = 0;
       olab = a.x;
+      graph = __int_as_float(a.y);
     } else {
-      a = __ldg(P.e_arc + arc);
-      ilab = a.x;
-      olab = a.w;
+      const int2 iw = __ldg(P.e_iw + arc);
+      const int2 no = __ldg(P.e_no + arc);
+      ilab = iw.x;
+      olab = no.y;
+      graph = __int_as_float(iw.y);
     }
     float tot = static_cast<float>(c - pc);
-    float graph = __int_as_float(a.y);
     il[pos] = ilab;
     ol[pos] = olab;
     gw[pos] = graph;
