@@ -87,6 +87,7 @@ typedef struct kd_stats {
   int64_t cycles_closure;  /* epsilon closure                                     */
   int64_t cycles_commit;   /* token block commit + table wipe                     */
   int64_t slots_claimed;   /* recombination-table slots claimed (>= tokens_out)   */
+  int64_t candidates;      /* emitting arcs that passed the running-cutoff filter */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

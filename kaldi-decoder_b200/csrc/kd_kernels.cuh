@@ -57,6 +57,7 @@ constexpr int32_t kEmptyKey = -1;
 constexpr unsigned long long kEmptyCost = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
+constexpr uint32_t kClassB = 0x80000000u;  // commit numbering: token goes behind the "good" ones
 
 struct __align__(16) HVal {
   unsigned long long cost;  // order-preserving image of the fp64 cost
@@ -89,6 +90,7 @@ struct __align__(16) LaneState {
   // SM cycles spent per phase (clock64 of thread 0), for the phase breakdown
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
+  long long st_cand;     // emitting arcs that passed the running-cutoff filter
   // best-path selection results
   int32_t bp_ok, bp_final, bp_best_state;
   uint32_t bp_best_tok;    // arena index
@@ -228,7 +230,8 @@ struct Shared {
   uint32_t list_n;
   uint32_t cand_n;
   uint32_t q_n[2];
-  uint32_t out_n;
+  uint32_t out_n;   // commit: tokens numbered in the front ("good") class
+  uint32_t out_b;   // commit: tokens numbered in the back class
   uint32_t count;
   uint32_t sel_bin, sel_k;
   int status;
@@ -525,16 +528,22 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
 // table is wiped, and the block's min cost is recorded for the next GetCutoff.
 // On entry queue 0 holds the slots, claimed during the emitting phase (or by
 // InitDecoding), whose states have epsilon arcs.
+//
+// The commit writes the tokens with cost < good_cut first: the next frame's
+// scan starts with them, so its running cutoff tightens early and few arcs
+// that the exact cutoff rejects become candidates.
 template <int THREADS>
 __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
-                                        LaneState &ls, double cstar) {
+                                        LaneState &ls, double cstar, double good_cut) {
   const int tid = threadIdx.x;
   const unsigned long long cstar_key = dkey(cstar);
+  const unsigned long long good_key = dkey(good_cut);
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const long long t_begin = clock64();
   if (tid == 0) {
     sh.q_n[1] = 0;
     sh.out_n = 0;
+    sh.out_b = 0;
     sh.acc_eps = 0;
   }
   __syncthreads();
@@ -578,18 +587,29 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     for (int u = 0; u < 4; ++u) {
       const bool live =
           v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
-      // warp-aggregated numbering: one shared-memory atomic per warp
-      const uint32_t live_mask = __ballot_sync(0xFFFFFFFFu, live);
-      uint32_t wbase = 0;
-      if ((tid & 31) == 0 && live_mask) wbase = atomicAdd(&sh.out_n, __popc(live_mask));
-      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-      if (h[u] != kNoIdx)
-        B.table[h[u]].idx =
-            live ? wbase + __popc(live_mask & ((1u << (tid & 31)) - 1u)) : kNoIdx;
+      const bool good = live && v[u].cost < good_key;
+      // warp-aggregated numbering within each class: one shared-memory atomic per warp
+      const uint32_t mask_a = __ballot_sync(0xFFFFFFFFu, good);
+      const uint32_t mask_b = __ballot_sync(0xFFFFFFFFu, live && !good);
+      uint32_t base_a = 0, base_b = 0;
+      if ((tid & 31) == 0) {
+        if (mask_a) base_a = atomicAdd(&sh.out_n, __popc(mask_a));
+        if (mask_b) base_b = atomicAdd(&sh.out_b, __popc(mask_b));
+      }
+      base_a = __shfl_sync(0xFFFFFFFFu, base_a, 0);
+      base_b = __shfl_sync(0xFFFFFFFFu, base_b, 0);
+      if (h[u] != kNoIdx) {
+        const uint32_t below = (1u << (tid & 31)) - 1u;
+        uint32_t idx = kNoIdx;
+        if (good) idx = base_a + __popc(mask_a & below);
+        else if (live) idx = kClassB | (base_b + __popc(mask_b & below));
+        B.table[h[u]].idx = idx;
+      }
     }
   }
   __syncthreads();
-  const uint32_t n_new = sh.out_n;
+  const uint32_t n_front = sh.out_n;
+  const uint32_t n_new = n_front + sh.out_b;
   const uint32_t new_base = ls.arena_used;
   if (static_cast<long long>(new_base) + n_new > P.arena_cap) {
     if (tid == 0) sh.status |= kStatusArenaOverflow;
@@ -624,21 +644,25 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       prev_idx[u] = 0;
-      if (h[u] != kNoIdx && static_cast<uint32_t>(meta[u].y) != kNoIdx && (v[u].arg >> 63) != 0)
-        prev_idx[u] = __ldcg(&B.table[static_cast<uint32_t>(v[u].arg)].idx);
+      if (h[u] != kNoIdx && static_cast<uint32_t>(meta[u].y) != kNoIdx && (v[u].arg >> 63) != 0) {
+        const uint32_t pi = __ldcg(&B.table[static_cast<uint32_t>(v[u].arg)].idx);
+        prev_idx[u] = (pi & kClassB) ? n_front + (pi & ~kClassB) : pi;
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (h[u] == kNoIdx) continue;
-      const uint32_t idx = static_cast<uint32_t>(meta[u].y);
+      uint32_t idx = static_cast<uint32_t>(meta[u].y);
+      if (idx != kNoIdx && (idx & kClassB)) idx = n_front + (idx & ~kClassB);
       if (idx != kNoIdx && write_ok) {
         const uint32_t arc = static_cast<uint32_t>(v[u].arg >> 32);
         uint32_t prev = static_cast<uint32_t>(v[u].arg);
         if (arc & kEpsFlag) prev = new_base + prev_idx[u];
         const double c = dunkey(v[u].cost);
-        B.a_cost[new_base + idx] = c;
-        B.a_link[new_base + idx] = (static_cast<unsigned long long>(arc) << 32) | prev;
-        B.a_state[new_base + idx] = meta[u].x;
+        // written once, read once next frame (cost, state) or at traceback (link)
+        __stcs(B.a_cost + new_base + idx, c);
+        __stcs(B.a_link + new_base + idx, (static_cast<unsigned long long>(arc) << 32) | prev);
+        __stcs(B.a_state + new_base + idx, meta[u].x);
         if (c < my_min) {
           my_min = c;
           my_arg = static_cast<int>(idx);
@@ -798,8 +822,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         tc[k] = inf;
         ts[k] = -1;
         if (i < static_cast<uint32_t>(n)) {
-          tc[k] = cost[i];
-          ts[k] = state[i];
+          tc[k] = __ldcs(cost + i);
+          ts[k] = __ldcs(state + i);
         }
       }
 #pragma unroll
@@ -849,17 +873,18 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     }
     if (tid == 0) t_ex[n_comp] = n_flat;
     __syncthreads();
-    // flat arc loop: this warp's slice is [jw0, jw1)
-    const uint32_t per_warp = ((n_flat + NW * 32 - 1) / (NW * 32)) * 32;
-    const uint32_t jw0 = warp * per_warp;
-    const uint32_t jw1 = min(n_flat, jw0 + per_warp);
-    if (jw0 < jw1) {
-      uint32_t t_lo = 0;  // compacted token owning arc jw0: largest t with t_ex[t] <= jw0
-#pragma unroll
-      for (int s = kSearchStep; s; s >>= 1)
-        if (t_lo + s < n_comp && t_ex[t_lo + s] <= jw0) t_lo += s;
+    // flat arc loop: steps of 32 * U arcs are dealt round-robin to the warps, so
+    // all warps start at the front of the flat space, where the commit put the
+    // tokens most likely to produce the frame's best arcs: the running cutoff
+    // is tight after the first round.
+    {
+      const uint32_t jw1 = n_flat;
 #pragma unroll 1
-      for (uint32_t jb = jw0; jb < jw1; jb += 32 * U) {
+      for (uint32_t jb = warp * (32 * U); jb < jw1; jb += NW * 32 * U) {
+        uint32_t t_lo = 0;  // compacted token owning arc jb: largest t with t_ex[t] <= jb
+#pragma unroll
+        for (int s = kSearchStep; s; s >>= 1)
+          if (t_lo + s < n_comp && t_ex[t_lo + s] <= jb) t_lo += s;
         int2 iw[U];
         uint32_t tt[U];
 #pragma unroll
@@ -904,8 +929,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const unsigned long long nk = dkey(nw[u]);
               const uint32_t e = atomicAdd(&sh.cand_n, 1u);
               if (e < P.ccap) {
-                B.cand[e] = make_uint4(static_cast<uint32_t>(nk), static_cast<uint32_t>(nk >> 32),
-                                       a, tok_abs);
+                __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
+                                              static_cast<uint32_t>(nk >> 32), a, tok_abs));
               } else {
                 insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
               }
@@ -935,8 +960,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   const unsigned long long cstar_key = dkey(cstar);
   // ---------------------------------------------------------------- recombine
   const uint32_t n_cand = min(sh.cand_n, P.ccap);
+  if (tid == 0) ls.st_cand += sh.cand_n;
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
-    const uint4 c = __ldcg(B.cand + e);
+    const uint4 c = __ldcs(B.cand + e);
     const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
     if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);
   }
@@ -999,7 +1025,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       else
         cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
                                                      t_beg, t_tok);
-      lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar);
+      // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
+      lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
+                                       cstar - 0.75 * static_cast<double>(P.beam));
       if (tid == 0) {
         ls.frames_decoded = frame + 1;
         ls.st_frames += 1;
@@ -1052,7 +1080,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
   }
   __syncthreads();
-  lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */);
+  lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */, 0.0);
   if (tid == 0) {
     ls.status = sh.status;
     ls.st_sweeps = 0;
