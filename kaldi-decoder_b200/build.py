@@ -60,7 +60,7 @@ def build_pybind(force: bool = False) -> str:
         return ""
     if force or _newer(out, srcs + hdrs + [os.path.join(LIB_DIR, "libkd_b200.so")]):
         _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fvisibility=hidden",
-              "-I" + os.path.join(ROOT, "include"), "-I" + HERE, "-I" + os.path.join(CSRC, "minifst"),
+              "-I" + os.path.join(ROOT, "include"), "-I" + ROOT, "-I" + os.path.join(CSRC, "minifst"),
               "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
               *srcs, "-L" + LIB_DIR, "-lkd_b200", "-Wl,-rpath,$ORIGIN/../../../lib", "-o", out])
     return out

@@ -43,3 +43,46 @@ def same_labels(a, b) -> bool:
 
 def rel_close(a: float, b: float, tol: float = 1e-4) -> bool:
     return abs(a - b) <= tol * max(1.0, abs(a), abs(b))
+
+
+GOLDEN_DIR = __import__("os").path.join(__import__("os").path.dirname(__file__), "golden")
+GOLDEN_CASES = ["h20_bind", "h20_default", "hl300", "hlg300_peaky", "hlg300_bind", "hlg300_nobeam"]
+
+
+class GoldenCase:
+    """One tests/golden/*.npz fixture (written by tests/golden/make_golden.py from oracle/_ref)."""
+
+    def __init__(self, name):
+        import os
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.z = z
+        self.name = name
+        self.graph = synth.Graph(int(z["num_states"]), int(z["start"]), z["row_off"], z["ilabel"],
+                                 z["olabel"], z["weight"], z["nextstate"], z["final"],
+                                 lm={"vocab": int(z["vocab"])}, name=name)
+        o = z["opts"]
+        self.opts = dict(beam=float(o[0]), max_active=int(o[1]), min_active=int(o[2]),
+                         beam_delta=float(o[3]), hash_ratio=float(o[4]))
+        self.n_utts, self.T = int(z["n_utts"]), int(z["T"])
+
+    def logp(self, u):
+        return self.z[f"logp{u}"]
+
+    def tokens(self, u):
+        """list over frames 0..T of (states, costs) in the reference's list order"""
+        n = self.z[f"tok_n{u}"]
+        st, co = self.z[f"tok_states{u}"], self.z[f"tok_costs{u}"]
+        out, p = [], 0
+        for k in n:
+            out.append((st[p:p + k], co[p:p + k]))
+            p += int(k)
+        return out
+
+    def best(self, u, use_final_probs=True):
+        t = "t" if use_final_probs else "f"
+        z = self.z
+        return kd_ref.BestPath(bool(z[f"ok_{t}{u}"]), z[f"il_{t}{u}"], z[f"ol_{t}{u}"],
+                               z[f"gw_{t}{u}"], z[f"aw_{t}{u}"], z[f"fin_{t}{u}"])
+
+    def reached_final(self, u):
+        return bool(self.z[f"reached_final{u}"])

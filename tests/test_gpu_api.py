@@ -1,0 +1,301 @@
+"""CUDA path through the C ABI and the drop-in Python API -- needs a B200."""
+import numpy as np
+import pytest
+
+from common import GOLDEN_CASES, GoldenCase, rel_close, same_labels, small_graph, sorted_tokens
+from kaldi_decoder_b200 import capi, synth
+from oracle import kd_oracle, kd_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _decoder(g, opts, lanes, **kw):
+    dg = capi.DeviceGraph.from_graph(g)
+    kw.setdefault("hash_capacity", 1 << 15)
+    kw.setdefault("arena_records", 1 << 20)
+    return capi.LaneDecoder(dg, capi.make_options(**opts), max_lanes=lanes, **kw)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_vectors_from_the_reference(name):
+    """Golden fixtures frozen from the unmodified reference: identical label sequences and
+    total cost (1e-4 relative) wherever the reference's pruning is order independent; on the
+    max_active-binding fixtures a differing utterance must be an exact cost tie or a binding
+    utterance."""
+    gc = GoldenCase(name)
+    dec = _decoder(gc.graph, gc.opts, gc.n_utts)
+    lanes = list(range(gc.n_utts))
+    dec.init(lanes)
+    dec.advance(lanes, [gc.logp(u) for u in lanes])
+    og = kd_oracle.OracleGraph(gc.graph)
+    for ufp in (True, False):
+        paths = dec.best_paths(lanes, ufp)
+        for u in lanes:
+            want = gc.best(u, ufp)
+            il, ol, gw, aw, fin = capi.merge_linear(paths[u])
+            assert paths[u].ok == want.ok
+            assert paths[u].reached_final == gc.reached_final(u)
+            o = kd_oracle.OracleDecoder(og, kd_ref.Options(**gc.opts), kd_oracle.REFERENCE_ORDER)
+            o.decode(gc.logp(u))
+            binding = o.stats()["binding_max"] > 0
+            identical = np.array_equal(il[il != 0], want.isyms) and \
+                np.array_equal(ol[ol != 0], want.osyms)
+            if not binding:
+                assert identical, (name, u, ufp)
+                assert rel_close(paths[u].total_cost, want.total_cost, 1e-4)
+                # RemoveEpsLocal grouping: same arcs, same per-arc weights
+                assert np.array_equal(il, want.ilabels) and np.array_equal(ol, want.olabels)
+                assert np.allclose(gw, want.graph, rtol=0, atol=1e-5)
+                assert np.allclose(aw, want.acoustic, rtol=0, atol=1e-3)
+                assert np.allclose(fin, want.final, rtol=0, atol=1e-6)
+            elif not identical:
+                # order-dependent pruning (the reference's result depends on its HashList
+                # order once max_active binds): the device must then equal the
+                # order-independent statement of the search exactly
+                c = kd_oracle.OracleDecoder(og, kd_ref.Options(**gc.opts), kd_oracle.CANONICAL)
+                c.decode(gc.logp(u))
+                cb = c.get_best_path(ufp, raw=True)
+                assert same_labels(paths[u], cb), (name, u, ufp)
+                assert rel_close(paths[u].total_cost, cb.total_cost, 1e-6)
+
+
+def test_identical_to_reference_on_peaky_hlg():
+    """Bigger differential test against oracle/_ref (or the oracle's reference-order mode when
+    the compiled reference is absent): 32 utterances, T=300."""
+    g = synth.make_hlg(5000, (200, 400), 100, seed=21)
+    opts = dict(beam=20.0, max_active=7000, min_active=20)
+    n, T = 32, 300
+    mats = [synth.make_logprobs(g, T, seed=900 + u, peak=12) for u in range(n)]
+    dec = _decoder(g, opts, n, hash_capacity=1 << 17, arena_records=1 << 21)
+    lanes = list(range(n))
+    dec.init(lanes)
+    dec.advance(lanes, mats)
+    paths = dec.best_paths(lanes, True)
+    if kd_ref.available():
+        rg = kd_ref.RefGraph(g)
+        _, ref_paths, rf = kd_ref.decode_batch(rg, np.stack(mats), kd_ref.Options(**opts), 8)
+    else:
+        og = kd_oracle.OracleGraph(g)
+        _, ref_paths, rf, _, _ = kd_oracle.decode_batch(og, np.stack(mats), kd_ref.Options(**opts), 8,
+                                                         kd_oracle.REFERENCE_ORDER)
+    diverged = 0
+    for u in lanes:
+        assert paths[u].reached_final == bool(rf[u])
+        if not same_labels(paths[u], ref_paths[u]):
+            diverged += 1
+            # a divergence is only acceptable as an exact tie in total cost
+            assert paths[u].total_cost == pytest.approx(ref_paths[u].total_cost, rel=1e-6)
+        assert rel_close(paths[u].total_cost, ref_paths[u].total_cost, 1e-4)
+    assert diverged == 0
+
+
+def test_streaming_chunks_equal_one_shot():
+    g = small_graph("HLG")
+    opts = dict(beam=16.0, max_active=2**31 - 1, min_active=20)
+    T = 120
+    lp = synth.make_logprobs(g, T, seed=4, peak=6)
+    dec = _decoder(g, opts, 2)
+    dec.init([0, 1])
+    dec.advance([0], [lp])
+    for a in range(0, T, 40):
+        chunk = lp[a:a + 40]
+        dec.advance([1], [chunk], offsets=[a], max_num_frames=15)
+        assert dec.num_frames_decoded(1) == a + 15
+        dec.advance([1], [chunk], offsets=[a])
+        assert dec.num_frames_decoded(1) == a + 40
+        # partial result is available at any time (GetBestPath mid-utterance)
+        assert dec.best_paths([1], True)[0].ok
+    s0, c0 = sorted_tokens(*dec.tokens(0))
+    s1, c1 = sorted_tokens(*dec.tokens(1))
+    assert np.array_equal(s0, s1) and np.array_equal(c0, c1)
+    p0, p1 = dec.best_paths([0, 1], True)
+    assert np.array_equal(p0.ilabels, p1.ilabels) and np.array_equal(p0.acoustic, p1.acoustic)
+
+
+def test_lanes_are_independent_and_reusable():
+    """The same utterance gives the same result in any lane, alone or in a batch, and a lane
+    can be re-initialised for a new utterance."""
+    g = small_graph("HL")
+    opts = dict(beam=20.0, max_active=7000, min_active=20)
+    mats = [synth.make_logprobs(g, 80, seed=u, peak=8) for u in range(5)]
+    dec = _decoder(g, opts, 8)
+    dec.init([0, 1, 2, 3, 4])
+    dec.advance([0, 1, 2, 3, 4], mats)
+    batch = dec.best_paths([0, 1, 2, 3, 4])
+    dec.init([7, 5])
+    dec.advance([7, 5], [mats[3], mats[1]])
+    again = dec.best_paths([7, 5])
+    for a, b in ((again[0], batch[3]), (again[1], batch[1])):
+        assert np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.olabels, b.olabels)
+        assert np.array_equal(a.graph, b.graph) and np.array_equal(a.acoustic, b.acoustic)
+    # ragged lengths in one call, zero-length included
+    dec.init([0, 1, 2])
+    dec.advance([0, 1, 2], [mats[0][:17], mats[1][:0], mats[2]])
+    assert [dec.num_frames_decoded(i) for i in (0, 1, 2)] == [17, 0, 80]
+    assert dec.best_paths([1])[0].ok and len(dec.best_paths([1])[0].ilabels) == 0
+
+
+def test_error_behaviour_matches_reference_assertions():
+    g = small_graph("H")
+    dg = capi.DeviceGraph.from_graph(g)
+    lp = synth.make_logprobs(g, 10, seed=1)
+    # faster-decoder.cc:24-28
+    for bad in (dict(hash_ratio=0.5), dict(max_active=1), dict(min_active=5, max_active=5)):
+        with pytest.raises(capi.KdError, match="Check failed"):
+            capi.LaneDecoder(dg, capi.make_options(**bad))
+    dec = capi.LaneDecoder(dg, capi.make_options(), max_lanes=2, hash_capacity=4096,
+                           arena_records=1 << 16)
+    # faster-decoder.cc:128-129
+    with pytest.raises(capi.KdError, match="InitDecoding"):
+        dec.advance([0], [lp])
+    dec.init([0])
+    dec.advance([0], [lp])
+    # faster-decoder.cc:137: fewer frames ready than decoded
+    with pytest.raises(capi.KdError, match="num_frames_ready >= num_frames_decoded_"):
+        dec.advance([0], [lp[:4]])
+    # ilabel beyond the decodable's columns (the reference reads out of bounds)
+    with pytest.raises(capi.KdError, match="columns"):
+        dec.advance([0], [np.zeros((12, 10), np.float32)])
+    with pytest.raises(capi.KdError, match="lane id"):
+        dec.init([2])
+    # a graph without start state (faster-decoder.cc:47)
+    with pytest.raises(capi.KdError, match="kNoStateId"):
+        capi.DeviceGraph(g.num_states, -1, g.row_off, g.ilabel, g.olabel, g.weight, g.nextstate,
+                         g.final)
+
+
+def test_capacity_overflow_is_a_hard_error_and_lane_recovers():
+    g = small_graph("HLG")
+    dg = capi.DeviceGraph.from_graph(g)
+    opts = capi.make_options(beam=30.0, max_active=2**31 - 1, min_active=0)
+    lp = synth.make_logprobs(g, 60, seed=2, peak=2)  # flat posteriors: thousands of tokens
+    dec = capi.LaneDecoder(dg, opts, max_lanes=1, hash_capacity=256, arena_records=1 << 20)
+    dec.init([0])
+    with pytest.raises(capi.KdError, match="overflow"):
+        dec.advance([0], [lp])
+    with pytest.raises(capi.KdError, match="error state"):
+        dec.advance([0], [lp])
+    small = capi.LaneDecoder(dg, opts, max_lanes=1, hash_capacity=1 << 16, arena_records=2000)
+    small.init([0])
+    with pytest.raises(capi.KdError, match="arena"):
+        small.advance([0], [lp])
+    # re-init clears the error; a narrow search then fits
+    dec.set_options(capi.make_options(beam=4.0, max_active=40, min_active=0))
+    dec.init([0])
+    dec.advance([0], [synth.make_logprobs(g, 30, seed=3, peak=14)])
+    assert dec.best_paths([0])[0].ok
+
+
+def test_degenerate_inputs():
+    """-inf log-probs drop arcs (inf < inf is false, faster-decoder.cc:211); when nothing
+    survives GetBestPath returns false (faster-decoder.cc:386-389)."""
+    g = small_graph("H")
+    opts = dict(beam=16.0, max_active=2**31 - 1, min_active=20)
+    dec = _decoder(g, opts, 2)
+    lp = synth.make_logprobs(g, 20, seed=5, peak=6)
+    dead = lp.copy()
+    dead[10, :] = -np.inf
+    dec.init([0, 1])
+    dec.advance([0, 1], [lp, dead])
+    p = dec.best_paths([0, 1])
+    assert p[0].ok and not p[1].ok and len(p[1].ilabels) == 0
+    assert dec.tokens(1)[0].size == 0 and not dec.reached_final(1)
+    og = kd_oracle.OracleGraph(g)
+    o = kd_oracle.OracleDecoder(og, kd_ref.Options(**opts), kd_oracle.REFERENCE_ORDER)
+    o.decode(dead)
+    assert not o.get_best_path().ok
+
+
+def test_drop_in_python_api_end_to_end():
+    """kaldi_decoder.FasterDecoder used as the icefall scripts use it, against the reference
+    result frozen in the golden fixture."""
+    import kaldi_decoder as kd
+    gc = GoldenCase("hlg300_peaky")
+    g = gc.graph
+    fst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                      g.weight, g.nextstate, g.final)
+    o = gc.opts
+    decoder = kd.FasterDecoder(fst, kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"],
+                                                            min_active=o["min_active"]))
+    for u in range(gc.n_utts):
+        decodable = kd.DecodableCtc(gc.logp(u))
+        decoder.decode(decodable)
+        assert decoder.num_frames_decoded() == gc.T
+        assert decoder.reached_final() == gc.reached_final(u)
+        ok, best = decoder.get_best_path()
+        want = gc.best(u, True)
+        assert ok == want.ok
+        ok2, isyms, osyms, (gcost, acost) = kd.get_linear_symbol_sequence(best)
+        assert ok2 and isyms == [int(x) for x in want.isyms] and osyms == [int(x) for x in want.osyms]
+        assert rel_close(gcost + acost, want.total_cost, 1e-4)
+        assert best.num_states == len(want.ilabels) + 1  # same RemoveEpsLocal grouping
+    # streaming with offsets + a Python-defined decodable
+    lp = gc.logp(0)
+
+    class PyDecodable(kd.DecodableInterface):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def log_likelihood(self, frame, index):
+            return float(self.m[frame, index - 1])
+
+        def is_last_frame(self, frame):
+            return frame == self.m.shape[0] - 1
+
+        def num_frames_ready(self):
+            return self.m.shape[0]
+
+        def num_indices(self):
+            return self.m.shape[1]
+
+    decoder.init_decoding()
+    decoder.advance_decoding(kd.DecodableCtc(lp[:30]), 10)
+    assert decoder.num_frames_decoded() == 10
+    decoder.advance_decoding(kd.DecodableCtc(lp[:30]))
+    decoder.advance_decoding(kd.DecodableCtc(lp[30:], offset=30))
+    ok, a = decoder.get_best_path()
+    decoder.decode(PyDecodable(lp))
+    ok, b = decoder.get_best_path()
+    assert kd.get_linear_symbol_sequence(a)[1:3] == kd.get_linear_symbol_sequence(b)[1:3]
+    with pytest.raises(RuntimeError):
+        kd.FasterDecoder(fst, kd.FasterDecoderOptions()).advance_decoding(kd.DecodableCtc(lp))
+    # batched additive API
+    bd = kd.BatchFasterDecoder(fst, kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"]),
+                               max_lanes=4)
+    bd.init_decoding([0, 1, 2])
+    bd.advance_decoding([0, 1, 2], [gc.logp(0), gc.logp(1), gc.logp(2)])
+    oks, lats = bd.get_best_paths([0, 1, 2])
+    for u in range(3):
+        assert oks[u]
+        assert kd.get_linear_symbol_sequence(lats[u])[2] == [int(x) for x in gc.best(u).osyms]
+
+
+def test_full_size_properties_on_the_bench_graph():
+    """BASELINE-size graph (HLG 3-gram, ~4.6M arcs), T=1000: determinism, lane-position
+    invariance and self-consistency of the returned costs (size-independent properties)."""
+    g = synth.make_config_graph("C3")
+    opts = dict(beam=20.0, max_active=7000, min_active=20)
+    n, T = 48, 1000
+    mats = [synth.make_logprobs(g, T, seed=7000 + u, peak=12) for u in range(n // 2)]
+    mats = mats + mats[::-1]  # every utterance appears in two different lanes
+    dec = _decoder(g, opts, n, hash_capacity=1 << 17, arena_records=1 << 22)
+    lanes = list(range(n))
+    dec.init(lanes)
+    dec.advance(lanes, mats)
+    first = dec.best_paths(lanes)
+    st1 = dec.stats()
+    dec.init(lanes)
+    dec.advance(lanes, mats)
+    second = dec.best_paths(lanes)
+    assert dec.stats()["emit_arcs"] == st1["emit_arcs"] and st1["frames"] == n * T
+    for u in lanes:
+        a, b, c = first[u], second[u], first[n - 1 - u]
+        for x in (b, c):
+            assert np.array_equal(a.ilabels, x.ilabels) and np.array_equal(a.olabels, x.olabels)
+            assert np.array_equal(a.graph, x.graph) and np.array_equal(a.acoustic, x.acoustic)
+        assert a.ok and (a.ilabels != 0).sum() == T  # one emitting arc per frame
+        # acoustic cost of the path == -sum of the log-probs it consumed (fp32 rounding per arc)
+        emit = a.ilabels != 0
+        lp = mats[u][np.arange(T), a.ilabels[emit] - 1].astype(np.float64)
+        assert abs(a.acoustic.astype(np.float64).sum() + lp.sum()) < 1e-2

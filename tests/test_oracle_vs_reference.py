@@ -1,0 +1,74 @@
+"""oracle/kd_oracle.cc (own restatement) against oracle/_ref (the unmodified reference
+object code).  Skipped where the compiled reference is not available."""
+import numpy as np
+import pytest
+
+from common import OPTION_SETS, same_labels, small_graph
+from kaldi_decoder_b200 import synth
+from oracle import kd_oracle, kd_ref
+
+pytestmark = pytest.mark.skipif(not kd_ref.available(), reason="oracle/_ref not built")
+
+
+@pytest.mark.parametrize("gname", ["H", "HL", "HLG"])
+@pytest.mark.parametrize("oi", range(len(OPTION_SETS)))
+def test_every_frame_token_list_is_identical(gname, oi):
+    g = small_graph(gname)
+    rg, og = kd_ref.RefGraph(g), kd_oracle.OracleGraph(g)
+    opts = kd_ref.Options(**OPTION_SETS[oi])
+    peak = [8, 4, 6, 3, 5][oi]
+    for seed in range(2):
+        lp = synth.make_logprobs(g, 100, seed=50 * oi + seed, peak=peak)
+        r = kd_ref.RefDecoder(rg, opts)
+        o = kd_oracle.OracleDecoder(og, opts, kd_oracle.REFERENCE_ORDER)
+        r.init_decoding()
+        o.init_decoding()
+        for f in range(100):
+            r.advance_decoding(lp, 0, 1)
+            o.advance_decoding(lp, 0, 1)
+            rs, rc = r.tokens()
+            os_, oc = o.tokens()
+            assert np.array_equal(rs, os_) and np.array_equal(rc, oc), (gname, oi, seed, f)
+        assert r.reached_final() == o.reached_final()
+        for ufp in (True, False):
+            a, b = r.get_best_path(ufp), o.get_best_path(ufp)
+            assert a.ok == b.ok
+            for x, y in ((a.ilabels, b.ilabels), (a.olabels, b.olabels), (a.graph, b.graph),
+                         (a.acoustic, b.acoustic), (a.final, b.final)):
+                assert np.array_equal(x, y)
+
+
+def test_streaming_chunks_and_object_reuse():
+    """advance_decoding in chunks with offsets == one shot; a decoder object reused for a
+    second utterance keeps the reference's persistent hash size (and still matches)."""
+    g = small_graph("HLG")
+    rg, og = kd_ref.RefGraph(g), kd_oracle.OracleGraph(g)
+    opts = kd_ref.Options(beam=12.0, max_active=200, min_active=20)
+    r = kd_ref.RefDecoder(rg, opts)
+    o = kd_oracle.OracleDecoder(og, opts, kd_oracle.REFERENCE_ORDER)
+    for seed in (3, 4):
+        lp = synth.make_logprobs(g, 90, seed=seed, peak=4)
+        r.init_decoding()
+        o.init_decoding()
+        for a in range(0, 90, 30):
+            r.advance_decoding(lp[a:a + 30], a, -1)
+            o.advance_decoding(lp[a:a + 30], a, 7)
+            o.advance_decoding(lp[a:a + 30], a, -1)
+            assert r.num_frames_decoded() == o.num_frames_decoded() == a + 30
+            rs, rc = r.tokens()
+            os_, oc = o.tokens()
+            assert np.array_equal(rs, os_) and np.array_equal(rc, oc)
+        assert same_labels(r.get_best_path(), o.get_best_path())
+
+
+def test_batch_entry_points_agree():
+    g = small_graph("HL")
+    rg, og = kd_ref.RefGraph(g), kd_oracle.OracleGraph(g)
+    opts = kd_ref.Options(beam=20.0, max_active=7000)
+    mats = synth.make_batch(g, 6, 80, seed=9, peak=8)
+    _, rp, rrf = kd_ref.decode_batch(rg, mats, opts, 3)
+    _, op, orf, stats, per = kd_oracle.decode_batch(og, mats, opts, 3, kd_oracle.REFERENCE_ORDER)
+    assert np.array_equal(rrf, orf)
+    for a, b in zip(rp, op):
+        assert np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.acoustic, b.acoustic)
+    assert stats["frames"] == 6 * 80 and per.shape[0] == 6
