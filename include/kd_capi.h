@@ -88,6 +88,8 @@ typedef struct kd_stats {
   int64_t cycles_commit;   /* token block commit + table wipe                     */
   int64_t slots_claimed;   /* recombination-table slots claimed (>= tokens_out)   */
   int64_t candidates;      /* emitting arcs that passed the running-cutoff filter */
+  int64_t arcs_evaluated;  /* arcs actually loaded: scanned, or found through a label
+                              table; emit_arcs - this = arcs skipped as provably pruned */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

@@ -57,7 +57,9 @@ struct kd_graph {
   // one device allocation, hottest arrays first: [e_iw | st | e_no | n_arc | fin]
   unsigned char *blob = nullptr;
   size_t blob_bytes = 0;
-  int4 *st = nullptr;
+  int64_t num_label_tables = 0;
+  uint16_t *labtab = nullptr;  // [num_label_tables][max_ilabel]: ilabel-1 -> arc offset in its state
+  int4 *st = nullptr;          // 2 x int4 per state
   int2 *e_iw = nullptr;
   int2 *e_no = nullptr;
   int4 *n_arc = nullptr;
@@ -133,6 +135,8 @@ kd::Params MakeParams(const kd_decoder *d) {
   kd::Params P;
   memset(&P, 0, sizeof(P));
   P.st = d->g->st;
+  P.labtab = d->g->labtab;
+  P.lab_stride = d->g->max_ilabel;
   P.e_iw = d->g->e_iw;
   P.e_no = d->g->e_no;
   P.n_arc = d->g->n_arc;
@@ -174,7 +178,7 @@ template <int THREADS, int MIN_BLOCKS>
 int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
   size_t smem = kd::advance_smem_fixed<THREADS>() + 16;
   if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(double);
-  if (smem > 48 * 1024)
+  if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default limit too
     KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
@@ -279,12 +283,15 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   if (device < 0 || device >= ndev) return Fail(KD_ERR_INVALID, "device index out of range");
   KD_CUDA(cudaSetDevice(device));
 
-  std::vector<int4> st(num_states);
+  // st[2s] = {emit_begin, emit_count, eps_begin, eps_count}
+  // st[2s+1] = {label-table row or -1, bits of the smallest emitting weight, 0, 0}
+  std::vector<int4> st(2 * static_cast<size_t>(num_states));
   int64_t n_emit = 0, n_eps = 0;
   int32_t max_il = 0;
   for (int32_t s = 0; s < num_states; ++s) {
     if (row_offsets[s + 1] < row_offsets[s]) return Fail(KD_ERR_INVALID, "bad row_offsets");
     int64_t ne = 0, nn = 0;
+    float wmin = std::numeric_limits<float>::infinity();
     for (int64_t a = row_offsets[s]; a < row_offsets[s + 1]; ++a) {
       if (ilabel[a] < 0) return Fail(KD_ERR_INVALID, "negative ilabel");
       if (nextstate[a] < 0 || nextstate[a] >= num_states)
@@ -292,14 +299,59 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
       if (ilabel[a] != 0) {
         ++ne;
         max_il = std::max(max_il, ilabel[a]);
+        if (weight[a] < wmin) wmin = weight[a];  // NaN weights never lower it: no label table then
+        if (!(weight[a] == weight[a])) wmin = -std::numeric_limits<float>::infinity();
       } else {
         ++nn;
       }
     }
-    st[s] = make_int4(static_cast<int>(n_emit), static_cast<int>(ne),
-                      static_cast<int>(n_eps), static_cast<int>(nn));
+    int wmin_bits;
+    memcpy(&wmin_bits, &wmin, 4);
+    st[2 * static_cast<size_t>(s)] = make_int4(static_cast<int>(n_emit), static_cast<int>(ne),
+                                               static_cast<int>(n_eps), static_cast<int>(nn));
+    st[2 * static_cast<size_t>(s) + 1] = make_int4(-1, wmin_bits, 0, 0);
     n_emit += ne;
     n_eps += nn;
+  }
+  // Label tables: for states with many emitting arcs and distinct ilabels, a row
+  // ilabel-1 -> offset of that arc within the state.  A token whose slack
+  // (cutoff - cost - smallest weight) only admits the few best labels of the frame
+  // looks those labels up instead of scanning all its arcs.
+  std::vector<uint16_t> labtab;
+  int64_t n_tab = 0;
+  if (max_il > 0 && max_il <= 65535 && getenv("KD_B200_NO_LABEL_TABLES") == nullptr) {
+    std::vector<std::pair<int32_t, int32_t>> cands;  // (emit count, state)
+    for (int32_t s = 0; s < num_states; ++s) {
+      const int ne = st[2 * static_cast<size_t>(s)].y;
+      if (ne >= kd::kLabelTableMinDegree && ne < 65535) cands.emplace_back(ne, s);
+    }
+    std::sort(cands.begin(), cands.end(), [](const std::pair<int32_t, int32_t> &a,
+                                             const std::pair<int32_t, int32_t> &b) {
+      return a.first != b.first ? a.first > b.first : a.second < b.second;
+    });
+    const size_t row_bytes = static_cast<size_t>(max_il) * sizeof(uint16_t);
+    const size_t budget = std::max<size_t>(64u << 20, static_cast<size_t>(n_emit) * 4);
+    std::vector<int32_t> stamp(static_cast<size_t>(max_il) + 1, -1);
+    for (const auto &c : cands) {
+      if ((static_cast<size_t>(n_tab) + 1) * row_bytes > budget) break;
+      const int32_t s = c.second;
+      bool distinct = true;
+      for (int64_t a = row_offsets[s]; a < row_offsets[s + 1] && distinct; ++a) {
+        if (ilabel[a] == 0) continue;
+        if (stamp[ilabel[a]] == s) distinct = false;
+        stamp[ilabel[a]] = s;
+      }
+      if (!distinct) continue;
+      labtab.resize((static_cast<size_t>(n_tab) + 1) * max_il, 0xFFFFu);
+      uint16_t *row = labtab.data() + static_cast<size_t>(n_tab) * max_il;
+      uint16_t off = 0;
+      for (int64_t a = row_offsets[s]; a < row_offsets[s + 1]; ++a) {
+        if (ilabel[a] == 0) continue;
+        row[ilabel[a] - 1] = off++;
+      }
+      st[2 * static_cast<size_t>(s) + 1].x = static_cast<int>(n_tab);
+      ++n_tab;
+    }
   }
   if (n_emit >= 0x7FFFFFFFll || n_eps >= 0x7FFFFFFFll)
     return Fail(KD_ERR_INVALID, "graph too large (2^31 arcs)");
@@ -312,7 +364,9 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
       int wbits;
       memcpy(&wbits, &weight[a], 4);
       const int32_t ns = nextstate[a];
-      const int ns_word = st[ns].w > 0 ? static_cast<int>(static_cast<uint32_t>(ns) | kd::kEpsFlag) : ns;
+      const int ns_word = st[2 * static_cast<size_t>(ns)].w > 0
+                              ? static_cast<int>(static_cast<uint32_t>(ns) | kd::kEpsFlag)
+                              : ns;
       if (ilabel[a] != 0) {
         eiw[ie] = make_int2(ilabel[a], wbits);
         eno[ie] = make_int2(ns_word, olabel[a]);
@@ -334,8 +388,10 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   auto round256 = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   const size_t b_iw = round256(eiw.size() * sizeof(int2)), b_st = round256(st.size() * sizeof(int4)),
                b_no = round256(eno.size() * sizeof(int2)), b_na = round256(na.size() * sizeof(int4)),
-               b_fin = round256(static_cast<size_t>(num_states) * sizeof(float));
-  g->blob_bytes = b_iw + b_st + b_no + b_na + b_fin;
+               b_fin = round256(static_cast<size_t>(num_states) * sizeof(float)),
+               b_tab = round256(labtab.size() * sizeof(uint16_t));
+  g->blob_bytes = b_iw + b_st + b_no + b_na + b_fin + b_tab;
+  g->num_label_tables = n_tab;
   if ((rc = DevAlloc(&g->blob, g->blob_bytes))) {
     kd_graph_destroy(g);
     return rc;
@@ -345,6 +401,10 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   g->e_no = reinterpret_cast<int2 *>(g->blob + b_iw + b_st);
   g->n_arc = reinterpret_cast<int4 *>(g->blob + b_iw + b_st + b_no);
   g->fin = reinterpret_cast<float *>(g->blob + b_iw + b_st + b_no + b_na);
+  g->labtab = reinterpret_cast<uint16_t *>(g->blob + b_iw + b_st + b_no + b_na + b_fin);
+  if (!labtab.empty())
+    KD_CUDA(cudaMemcpy(g->labtab, labtab.data(), labtab.size() * sizeof(uint16_t),
+                       cudaMemcpyHostToDevice));
   KD_CUDA(cudaMemcpy(g->st, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice));
   if (!eiw.empty()) {
     KD_CUDA(cudaMemcpy(g->e_iw, eiw.data(), eiw.size() * sizeof(int2), cudaMemcpyHostToDevice));
@@ -894,6 +954,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->cycles_commit += L.cyc_commit;
     out->slots_claimed += L.st_claimed;
     out->candidates += L.st_cand;
+    out->arcs_evaluated += L.st_items;
   }
   return KD_OK;
 }

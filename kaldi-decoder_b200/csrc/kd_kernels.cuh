@@ -57,7 +57,10 @@ constexpr int32_t kEmptyKey = -1;
 constexpr unsigned long long kEmptyCost = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
-constexpr uint32_t kClassB = 0x80000000u;  // commit numbering: token goes behind the "good" ones
+constexpr uint32_t kClassB = 0x80000000u;
+constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
+constexpr int kTopLabels = 32;            // best labels of a frame kept for label-table lookups
+constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
 struct __align__(16) HVal {
   unsigned long long cost;  // order-preserving image of the fp64 cost
@@ -91,6 +94,7 @@ struct __align__(16) LaneState {
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
+  long long st_items;    // arcs actually evaluated (scanned + looked up)
   // best-path selection results
   int32_t bp_ok, bp_final, bp_best_state;
   uint32_t bp_best_tok;    // arena index
@@ -111,7 +115,10 @@ struct Params {
   // graph (device): CSR split into emitting and epsilon arcs.  The scan of the
   // emitting arcs only needs (ilabel, weight): they are an 8-byte array of
   // their own; (nextstate, olabel) are read for admitted arcs only.
-  const int4 *st;      // [S]  {emit_begin, emit_count, eps_begin, eps_count}
+  const int4 *st;      // [2S] {emit_begin, emit_count, eps_begin, eps_count},
+                       //      {label-table row or -1, smallest emitting weight bits, 0, 0}
+  const uint16_t *labtab;  // [rows][lab_stride]: ilabel-1 -> arc offset within the state, 0xFFFF none
+  int32_t lab_stride;
   const int2 *e_iw;    // [Ee] {ilabel, weight bits}
   const int2 *e_no;    // [Ee] {nextstate | kEpsFlag if that state has eps arcs, olabel}
   const int4 *n_arc;   // [En] {olabel, weight bits, nextstate | kEpsFlag ..., 0}
@@ -234,6 +241,13 @@ struct Shared {
   uint32_t out_b;   // commit: tokens numbered in the back class
   uint32_t count;
   uint32_t sel_bin, sel_k;
+  // the frame's best labels (smallest -log-prob), ascending; complete below top_tau
+  float top_ac[kTopLabels];
+  uint16_t top_lab[kTopLabels];
+  uint32_t top_n;
+  float top_tau;
+  uint32_t top_cnt[4];
+  uint32_t acc_items;
   int status;
   int item;
 };
@@ -510,7 +524,7 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(v.cost < cstar_key || is_eps)) return;
   const int32_t state = __ldcg(&B.table[slot].key);
-  const int4 st = __ldg(P.st + state);
+  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(state));
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
   *eps_count += static_cast<uint32_t>(st.w);
@@ -755,7 +769,7 @@ template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
                                        LaneState &ls, const float *row_g, double *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
-                                       uint16_t *t_tok) {
+                                       int32_t *t_tab, uint16_t *t_tok) {
   constexpr int U = kWindows;
   constexpr int TT = THREADS * 4;
   constexpr int NW = THREADS / 32;
@@ -777,19 +791,83 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   }
   if (tid == 0) {
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
-    sh.acc_emit = sh.acc_expanded = 0;
+    sh.acc_emit = sh.acc_expanded = sh.acc_items = 0;
     sh.cand_n = 0;
+    sh.top_n = 0;
+    sh.top_cnt[0] = sh.top_cnt[1] = sh.top_cnt[2] = sh.top_cnt[3] = 0;
   }
   double wc;
   float abf;
   lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &abf);
   const double ab = static_cast<double>(abf);
   __syncthreads();
+  // The frame's best labels: all labels with -log-prob below top_tau, at most
+  // kTopLabels of them, sorted.  A token whose slack admits only labels below
+  // top_tau looks them up in its state's label table instead of scanning its arcs.
+  {
+    float amin = __int_as_float(0x7F800000);
+    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, -__ldg(row_g + i));
+    double dmin;
+    int dummy;
+    block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
+    amin = static_cast<float>(dmin);
+    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int i = tid; i < P.cols; i += THREADS) {
+      const float d = -__ldg(row_g + i) - amin;
+      c0 += d < 2.0f;
+      c1 += d < 4.0f;
+      c2 += d < 8.0f;
+      c3 += d < 12.0f;
+    }
+    c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
+    c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
+    c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
+    c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
+    if (lane == 0) {
+      atomicAdd(&sh.top_cnt[0], c0);
+      atomicAdd(&sh.top_cnt[1], c1);
+      atomicAdd(&sh.top_cnt[2], c2);
+      atomicAdd(&sh.top_cnt[3], c3);
+    }
+    __syncthreads();
+    float delta = 0.0f;  // widest band holding at most kTopLabels labels
+    if (sh.top_cnt[3] <= kTopLabels) delta = 12.0f;
+    else if (sh.top_cnt[2] <= kTopLabels) delta = 8.0f;
+    else if (sh.top_cnt[1] <= kTopLabels) delta = 4.0f;
+    else if (sh.top_cnt[0] <= kTopLabels) delta = 2.0f;
+    const float tau = delta > 0.0f ? amin + delta : __int_as_float(0xFF800000);  // -inf: none
+    for (int i = tid; i < P.cols; i += THREADS) {
+      const float a = -__ldg(row_g + i);
+      if (a - amin < delta) {
+        const uint32_t e = atomicAdd(&sh.top_n, 1u);
+        sh.top_ac[e] = a;
+        sh.top_lab[e] = static_cast<uint16_t>(i + 1);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // rank sort of <= 32 entries
+      const uint32_t m = sh.top_n;
+      const float a = lane < m ? sh.top_ac[lane] : 0.0f;
+      const uint16_t l = lane < m ? sh.top_lab[lane] : 0;
+      uint32_t rank = 0;
+      for (uint32_t k = 0; k < m; ++k) {
+        const float b = sh.top_ac[k];
+        rank += (b < a) || (b == a && k < static_cast<uint32_t>(lane));
+      }
+      __syncwarp();
+      if (lane < m) {
+        sh.top_ac[rank] = a;
+        sh.top_lab[rank] = l;
+      }
+      if (lane == 0) sh.top_tau = tau;
+    }
+    __syncthreads();
+  }
 
   // seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189)
   double seed = inf;
   if (n > 0 && ls.best_cost < wc) {
-    const int4 st = __ldg(P.st + state[ls.best_idx]);
+    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(state[ls.best_idx]));
     for (int a = tid; a < st.y; a += THREADS) {
       const int2 iw = __ldg(P.e_iw + st.x + a);
       const double ac = ROW_SMEM ? s_row[iw.x - 1] : widen(-__ldg(row_g + iw.x - 1));
@@ -813,6 +891,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     // tile setup: 4 consecutive tokens per thread -> compacted (cost, arc
     // range, arc prefix) of the tokens to expand
     uint32_t cnt[4], beg[4];
+    int32_t tab[4];
     double tc[4];
     {
       int32_t ts[4];
@@ -827,15 +906,41 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         }
       }
 #pragma unroll
+      int4 sa[4], sb[4];
+#pragma unroll
       for (int k = 0; k < 4; ++k) {
-        cnt[k] = 0;
-        beg[k] = 0;
+        sa[k] = make_int4(0, 0, 0, 0);
+        sb[k] = make_int4(-1, 0, 0, 0);
         if (ts[k] >= 0 && tc[k] < wc) {  // faster-decoder.cc:202
-          const int4 st = __ldg(P.st + ts[k]);
-          beg[k] = static_cast<uint32_t>(st.x);
-          cnt[k] = static_cast<uint32_t>(st.y);
+          sa[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]));
+          sb[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]) + 1);
+        }
+      }
+      // a valid bound on this frame's final cutoff (the seeded running cutoff)
+      const double cut_seed = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
+      const float tau = sh.top_tau;
+      const uint32_t top_n = sh.top_n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        beg[k] = static_cast<uint32_t>(sa[k].x);
+        cnt[k] = static_cast<uint32_t>(sa[k].y);  // work items: arcs, or labels to look up
+        tab[k] = -1;
+        if (ts[k] >= 0 && tc[k] < wc) {
           ++n_expanded;
           n_arcs += cnt[k];
+          if (sb[k].x >= 0) {
+            // an arc can only pass if ac < cutoff - cost - w <= slack (margin for fp rounding)
+            const double slack = (cut_seed - tc[k]) - widen(__int_as_float(sb[k].y));
+            const float sf = __double2float_ru(slack + 1e-6 * (fabs(cut_seed) + 1.0));
+            if (sf <= tau) {
+              uint32_t kk = 0;  // labels of the sorted list with ac < sf
+              for (uint32_t q = 0; q < top_n; ++q) kk += sh.top_ac[q] < sf;
+              if (2 * kk < cnt[k]) {
+                tab[k] = sb[k].x;
+                cnt[k] = kk;
+              }
+            }
+          }
         }
       }
     }
@@ -864,14 +969,18 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     for (int k = 0; k < 4; ++k) {
       if (cnt[k] != 0) {
         t_ex[ex_toks] = ex_arcs;
-        t_beg[ex_toks] = beg[k];
+        t_beg[ex_toks] = beg[k] | (tab[k] >= 0 ? kLookupFlag : 0u);
+        t_tab[ex_toks] = tab[k];
         t_cost[ex_toks] = tc[k];
         t_tok[ex_toks] = static_cast<uint16_t>(4 * tid + k);
         ex_arcs += cnt[k];
         ++ex_toks;
       }
     }
-    if (tid == 0) t_ex[n_comp] = n_flat;
+    if (tid == 0) {
+      t_ex[n_comp] = n_flat;
+      sh.acc_items += n_flat;
+    }
     __syncthreads();
     // flat arc loop: steps of 32 * U arcs are dealt round-robin to the warps, so
     // all warps start at the front of the flat space, where the commit put the
@@ -886,25 +995,53 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         for (int s = kSearchStep; s; s >>= 1)
           if (t_lo + s < n_comp && t_ex[t_lo + s] <= jb) t_lo += s;
         int2 iw[U];
-        uint32_t tt[U];
+        uint32_t tt[U];   // compacted token of the item, kNoIdx if none
+        uint32_t aa[U];   // emitting arc index of the item, kNoIdx if none
+        uint32_t lk[U];   // lookup items: label-table value (fetched in stage 1)
+        // stage 1: item -> token; lookup items fetch their label-table entry
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const uint32_t j0 = jb + 32 * u;
           const uint32_t j = j0 + lane;
-          iw[u] = make_int2(1, 0);
           tt[u] = kNoIdx;
+          aa[u] = kNoIdx;
+          lk[u] = 0xFFFFu;
           if (j0 < jw1) {  // warp-uniform
-            // boundaries (first arc index) of the 32 tokens after t_lo
+            // boundaries (first item index) of the 32 tokens after t_lo
             const uint32_t bnd = t_ex[min(t_lo + 1 + lane, n_comp)];
-            const uint32_t p = bnd - j0;  // >= 1: token t_lo owns arc j0
+            const uint32_t p = bnd - j0;  // >= 1: token t_lo owns item j0
             const uint32_t mask = __reduce_or_sync(0xFFFFFFFFu, p < 32 ? (1u << p) : 0u);
             const bool edge = __any_sync(0xFFFFFFFFu, p == 32);
             const uint32_t t = t_lo + __popc(mask & ((2u << lane) - 1u));
             if (j < jw1) {
               tt[u] = t;
-              iw[u] = __ldg(P.e_iw + t_beg[t] + (j - t_ex[t]));
+              const uint32_t b = t_beg[t];
+              const uint32_t k = j - t_ex[t];
+              if (b & kLookupFlag) {
+                const uint32_t lab = sh.top_lab[k];
+                lk[u] = __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
+                aa[u] = b & ~kLookupFlag;  // base; the offset is added in stage 2
+              } else {
+                aa[u] = b + k;
+              }
             }
             t_lo += __popc(mask) + (edge ? 1u : 0u);
+          }
+        }
+        // stage 2: arc loads
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          iw[u] = make_int2(1, 0);
+          if (tt[u] != kNoIdx) {
+            if (t_beg[tt[u]] & kLookupFlag) {
+              if (lk[u] == 0xFFFFu) {
+                tt[u] = kNoIdx;  // the state has no arc with this label
+                aa[u] = kNoIdx;
+              } else {
+                aa[u] += lk[u];
+              }
+            }
+            if (aa[u] != kNoIdx) iw[u] = __ldg(P.e_iw + aa[u]);
           }
         }
         const double cut_d = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
@@ -922,9 +1059,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             if (adm & (1u << u)) {
-              const uint32_t j = jb + 32 * u + lane;
               const uint32_t t = tt[u];
-              const uint32_t a = t_beg[t] + (j - t_ex[t]);
+              const uint32_t a = aa[u];
               const uint32_t tok_abs = base + tile0 + t_tok[t];
               const unsigned long long nk = dkey(nw[u]);
               const uint32_t e = atomicAdd(&sh.cand_n, 1u);
@@ -982,6 +1118,7 @@ template <int THREADS>
 __host__ __device__ constexpr size_t advance_smem_fixed() {
   return THREADS * 4 * (sizeof(double) + 4) +  // t_cost, t_beg
          (THREADS * 4 + 4) * 4 +               // t_ex
+         THREADS * 4 * 4 +                     // t_tab
          THREADS * 4 * 2;                      // t_tok
 }
 
@@ -996,7 +1133,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
   double *t_cost = reinterpret_cast<double *>(dyn_smem);
   uint32_t *t_beg = reinterpret_cast<uint32_t *>(t_cost + TT);
   uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
-  uint16_t *t_tok = reinterpret_cast<uint16_t *>(t_ex + TT + 4);
+  int32_t *t_tab = reinterpret_cast<int32_t *>(t_ex + TT + 4);
+  uint16_t *t_tok = reinterpret_cast<uint16_t *>(t_tab + TT);
   double *s_row = reinterpret_cast<double *>(t_tok + TT);  // TT * 2 bytes: 8-byte aligned
   const int tid = threadIdx.x;
 
@@ -1021,10 +1159,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       double cstar;
       if (P.row_in_smem)
         cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
-                                                    t_beg, t_tok);
+                                                    t_beg, t_tab, t_tok);
       else
         cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
-                                                     t_beg, t_tok);
+                                                     t_beg, t_tab, t_tok);
       // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
                                        cstar - 0.75 * static_cast<double>(P.beam));
@@ -1035,6 +1173,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
         ls.st_tokens_out += ls.n_tok;
         ls.st_emit_arcs += sh.acc_emit;
         ls.st_expanded += sh.acc_expanded;
+        ls.st_items += sh.acc_items;
         if (ls.n_tok > ls.st_max_tokens) ls.st_max_tokens = ls.n_tok;
       }
       __syncthreads();
@@ -1071,7 +1210,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
   }
   __syncthreads();
   if (tid == 0) {
-    const int4 st = __ldg(P.st + P.start);
+    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(P.start));
     const uint32_t h =
         table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
     HVal v;

@@ -38,7 +38,8 @@ class KdStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("frames", "tokens_in", "tokens_expanded", "emit_arcs",
                                          "eps_arcs", "tokens_out", "max_tokens", "eps_sweeps",
                                          "cycles_cutoff", "cycles_expand", "cycles_closure",
-                                         "cycles_commit", "slots_claimed", "candidates")]
+                                         "cycles_commit", "slots_claimed", "candidates",
+                                         "arcs_evaluated")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

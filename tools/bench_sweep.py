@@ -28,7 +28,7 @@ for spec in sys.argv[1:]:
         c = d["roofline"]["counters"]
         f = max(1, c["frames"])
         per = {k: int(c[k] / f) for k in c if k.startswith("cycles") or k in
-               ("tokens_out", "emit_arcs", "slots_claimed", "candidates")}
+               ("tokens_out", "emit_arcs", "slots_claimed", "candidates", "arcs_evaluated")}
         print(f"[{spec}] fps={int(d['value'])} kernel_ms={d['roofline']['kernel_ms']:.1f} "
               f"GB/s={d['roofline']['achieved']:.0f} per-frame={per}", flush=True)
     except Exception as e:  # noqa: BLE001
