@@ -84,6 +84,7 @@ struct __align__(16) LaneState {
   int32_t frames_decoded;  // num_frames_decoded_; -1 before InitDecoding
   int32_t status;          // kStatus* bits; non-zero = lane unusable until init
   int32_t best_idx;        // index (in the current token block) of a best token
+  int32_t n_front;         // tokens at the front of the block that are close to the best
   uint32_t tok_base;       // arena index of the current token block
   uint32_t arena_used;     // arena records in use
   double best_cost;        // min cost over the current tokens (+inf if none)
@@ -703,6 +704,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.arena_used = new_base + n_new;
       ls.best_cost = bmin;
       ls.best_idx = barg;
+      ls.n_front = static_cast<int32_t>(n_front);
     } else {
       ls.n_tok = 0;
       ls.best_cost = inf;
@@ -887,7 +889,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // ---------------------------------------------------------------- scan
   uint32_t n_expanded = 0, n_arcs = 0;
   double my_min = inf;
-  for (uint32_t tile0 = 0; tile0 < static_cast<uint32_t>(n); tile0 += TT) {
+  // The first tile is the front class of the block (tokens close to the best,
+  // see the commit): scanning it first makes the running cutoff tight before the
+  // bulk of the tokens is classified (scan vs label lookup) and filtered.
+  const uint32_t first_tile =
+      ls.n_front > 0 ? min(static_cast<uint32_t>(ls.n_front), static_cast<uint32_t>(TT)) : TT;
+  for (uint32_t tile0 = 0, tile_end = min(static_cast<uint32_t>(n), first_tile);
+       tile0 < static_cast<uint32_t>(n);
+       tile0 = tile_end, tile_end = min(static_cast<uint32_t>(n), tile0 + TT)) {
     // tile setup: 4 consecutive tokens per thread -> compacted (cost, arc
     // range, arc prefix) of the tokens to expand
     uint32_t cnt[4], beg[4];
@@ -900,7 +909,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         const uint32_t i = tile0 + 4 * tid + k;
         tc[k] = inf;
         ts[k] = -1;
-        if (i < static_cast<uint32_t>(n)) {
+        if (i < tile_end) {
           tc[k] = __ldcs(cost + i);
           ts[k] = __ldcs(state + i);
         }
