@@ -775,8 +775,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   constexpr int U = kWindows;
   constexpr int TT = THREADS * 4;
   constexpr int NW = THREADS / 32;
-  constexpr int kSearchStep = TT > 2048 ? 2048 : TT > 1024 ? 1024 : TT > 512 ? 512 : 256;
-  static_assert(TT <= 4096 && TT > 256 && NW <= 16, "tile size out of range");
+  // 32-ary search over up to TT compacted tokens: strides 1024, 32, 1 (or 32, 1)
+  constexpr uint32_t kSearchTop = TT > 1024 ? 1024u : 32u;
+  static_assert(TT <= 32768 && NW <= 16, "tile size out of range");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const int n = ls.n_tok;
@@ -807,15 +808,18 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // kTopLabels of them, sorted.  A token whose slack admits only labels below
   // top_tau looks them up in its state's label table instead of scanning its arcs.
   {
+    // the row is in shared memory (already negated) when ROW_SMEM; the values are
+    // exact floats widened to fp64, so narrowing them back is lossless
     float amin = __int_as_float(0x7F800000);
-    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, -__ldg(row_g + i));
+    for (int i = tid; i < P.cols; i += THREADS)
+      amin = fminf(amin, ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i));
     double dmin;
     int dummy;
     block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
     amin = static_cast<float>(dmin);
     uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = -__ldg(row_g + i) - amin;
+      const float d = (ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i)) - amin;
       c0 += d < 2.0f;
       c1 += d < 4.0f;
       c2 += d < 8.0f;
@@ -839,7 +843,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     else if (sh.top_cnt[0] <= kTopLabels) delta = 2.0f;
     const float tau = delta > 0.0f ? amin + delta : __int_as_float(0xFF800000);  // -inf: none
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float a = -__ldg(row_g + i);
+      const float a = ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i);
       if (a - amin < delta) {
         const uint32_t e = atomicAdd(&sh.top_n, 1u);
         sh.top_ac[e] = a;
@@ -999,10 +1003,15 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       const uint32_t jw1 = n_flat;
 #pragma unroll 1
       for (uint32_t jb = warp * (32 * U); jb < jw1; jb += NW * 32 * U) {
-        uint32_t t_lo = 0;  // compacted token owning arc jb: largest t with t_ex[t] <= jb
+        // compacted token owning item jb = largest t with t_ex[t] <= jb: 32-ary search,
+        // every lane probes one position per level (t_ex[0] = 0 <= jb always)
+        uint32_t t_lo = 0;
 #pragma unroll
-        for (int s = kSearchStep; s; s >>= 1)
-          if (t_lo + s < n_comp && t_ex[t_lo + s] <= jb) t_lo += s;
+        for (uint32_t stride = kSearchTop; stride; stride >>= 5) {
+          const uint32_t pos = t_lo + lane * stride;
+          const bool le = pos < n_comp && t_ex[pos] <= jb;
+          t_lo += (__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u) * stride;
+        }
         int2 iw[U];
         uint32_t tt[U];   // compacted token of the item, kNoIdx if none
         uint32_t aa[U];   // emitting arc index of the item, kNoIdx if none
@@ -1109,7 +1118,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
     const uint4 c = __ldcs(B.cand + e);
     const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
-    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);
+    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);  // faster-decoder.cc:211, final cutoff
   }
   __syncthreads();
   if (tid == 0) {
