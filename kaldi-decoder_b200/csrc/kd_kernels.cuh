@@ -59,7 +59,8 @@ constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
 constexpr uint32_t kClassB = 0x80000000u;
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
-constexpr int kTopLabels = 32;            // best labels of a frame kept for label-table lookups
+constexpr int kOrderBins = 1024;          // buckets of the per-frame label order (1/32 wide)
+constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
 struct __align__(16) HVal {
@@ -242,12 +243,12 @@ struct Shared {
   uint32_t out_b;   // commit: tokens numbered in the back class
   uint32_t count;
   uint32_t sel_bin, sel_k;
-  // the frame's best labels (smallest -log-prob), ascending; complete below top_tau
-  float top_ac[kTopLabels];
-  uint16_t top_lab[kTopLabels];
-  uint32_t top_n;
-  float top_tau;
-  uint32_t top_cnt[4];
+  // the frame's labels ordered by bucket of their acoustic cost (-log-prob - minimum):
+  // labels with cost below a bound are lab_order[0 .. bin_start[bucket(bound) + 1])
+  uint16_t lab_order[kMaxOrderCols];
+  uint16_t bin_start[kOrderBins + 2];
+  float ac_min;
+  int order_ok;
   uint32_t acc_items;
   int status;
   int item;
@@ -796,80 +797,75 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
     sh.acc_emit = sh.acc_expanded = sh.acc_items = 0;
     sh.cand_n = 0;
-    sh.top_n = 0;
-    sh.top_cnt[0] = sh.top_cnt[1] = sh.top_cnt[2] = sh.top_cnt[3] = 0;
   }
   double wc;
   float abf;
   lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &abf);
   const double ab = static_cast<double>(abf);
   __syncthreads();
-  // The frame's best labels: all labels with -log-prob below top_tau, at most
-  // kTopLabels of them, sorted.  A token whose slack admits only labels below
-  // top_tau looks them up in its state's label table instead of scanning its arcs.
-  {
-    // the row is in shared memory (already negated) when ROW_SMEM; the values are
-    // exact floats widened to fp64, so narrowing them back is lossless
+  // Order the frame's labels by acoustic cost (counting sort into 1/32-wide buckets
+  // above the minimum).  A token whose slack admits few labels looks those labels up
+  // in its state's label table instead of scanning all its arcs.
+  if (ROW_SMEM && P.cols <= kMaxOrderCols && P.labtab != nullptr) {
+    uint32_t *hist = reinterpret_cast<uint32_t *>(t_cost);  // 2 * TT words, free until the scan
+    static_assert(2 * TT >= kOrderBins, "tile too small to hold the label histogram");
     float amin = __int_as_float(0x7F800000);
-    for (int i = tid; i < P.cols; i += THREADS)
-      amin = fminf(amin, ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i));
+    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, static_cast<float>(s_row[i]));
+    for (int b = tid; b < kOrderBins; b += THREADS) hist[b] = 0;
     double dmin;
     int dummy;
     block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
     amin = static_cast<float>(dmin);
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = (ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i)) - amin;
-      c0 += d < 2.0f;
-      c1 += d < 4.0f;
-      c2 += d < 8.0f;
-      c3 += d < 12.0f;
-    }
-    c0 = __reduce_add_sync(0xFFFFFFFFu, c0);
-    c1 = __reduce_add_sync(0xFFFFFFFFu, c1);
-    c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
-    c3 = __reduce_add_sync(0xFFFFFFFFu, c3);
-    if (lane == 0) {
-      atomicAdd(&sh.top_cnt[0], c0);
-      atomicAdd(&sh.top_cnt[1], c1);
-      atomicAdd(&sh.top_cnt[2], c2);
-      atomicAdd(&sh.top_cnt[3], c3);
+      const float d = (static_cast<float>(s_row[i]) - amin) * 32.0f;
+      const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
+      atomicAdd(&hist[b], 1u);
     }
     __syncthreads();
-    float delta = 0.0f;  // widest band holding at most kTopLabels labels
-    if (sh.top_cnt[3] <= kTopLabels) delta = 12.0f;
-    else if (sh.top_cnt[2] <= kTopLabels) delta = 8.0f;
-    else if (sh.top_cnt[1] <= kTopLabels) delta = 4.0f;
-    else if (sh.top_cnt[0] <= kTopLabels) delta = 2.0f;
-    const float tau = delta > 0.0f ? amin + delta : __int_as_float(0xFF800000);  // -inf: none
-    for (int i = tid; i < P.cols; i += THREADS) {
-      const float a = ROW_SMEM ? static_cast<float>(s_row[i]) : -__ldg(row_g + i);
-      if (a - amin < delta) {
-        const uint32_t e = atomicAdd(&sh.top_n, 1u);
-        sh.top_ac[e] = a;
-        sh.top_lab[e] = static_cast<uint16_t>(i + 1);
+    {
+      // exclusive prefix over the buckets, kOrderBins / THREADS consecutive ones per thread
+      constexpr int PER = (kOrderBins + THREADS - 1) / THREADS;
+      uint32_t loc[PER], sum = 0;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int b = tid * PER + k;
+        loc[k] = b < kOrderBins ? hist[b] : 0;
+        sum += loc[k];
+      }
+      uint32_t wtot;
+      uint32_t ex = warp_excl_scan(sum, &wtot);
+      if (lane == 0) sh.warp_sums[warp] = wtot;
+      __syncthreads();
+#pragma unroll
+      for (int w = 0; w < NW; ++w)
+        if (w < warp) ex += sh.warp_sums[w];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        const int b = tid * PER + k;
+        if (b < kOrderBins) {
+          sh.bin_start[b] = static_cast<uint16_t>(ex);
+          hist[b] = ex;  // scatter cursor
+          ex += loc[k];
+        }
+      }
+      if (tid == 0) {
+        sh.bin_start[kOrderBins] = static_cast<uint16_t>(P.cols);
+        sh.bin_start[kOrderBins + 1] = static_cast<uint16_t>(P.cols);
+        sh.ac_min = amin;
+        sh.order_ok = 1;
       }
     }
     __syncthreads();
-    if (warp == 0) {  // rank sort of <= 32 entries
-      const uint32_t m = sh.top_n;
-      const float a = lane < m ? sh.top_ac[lane] : 0.0f;
-      const uint16_t l = lane < m ? sh.top_lab[lane] : 0;
-      uint32_t rank = 0;
-      for (uint32_t k = 0; k < m; ++k) {
-        const float b = sh.top_ac[k];
-        rank += (b < a) || (b == a && k < static_cast<uint32_t>(lane));
-      }
-      __syncwarp();
-      if (lane < m) {
-        sh.top_ac[rank] = a;
-        sh.top_lab[rank] = l;
-      }
-      if (lane == 0) sh.top_tau = tau;
+    for (int i = tid; i < P.cols; i += THREADS) {
+      const float d = (static_cast<float>(s_row[i]) - amin) * 32.0f;
+      const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
+      sh.lab_order[atomicAdd(&hist[b], 1u)] = static_cast<uint16_t>(i + 1);
     }
+    __syncthreads();
+  } else {
+    if (tid == 0) sh.order_ok = 0;
     __syncthreads();
   }
-
   // seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189)
   double seed = inf;
   if (n > 0 && ls.best_cost < wc) {
@@ -931,8 +927,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       }
       // a valid bound on this frame's final cutoff (the seeded running cutoff)
       const double cut_seed = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
-      const float tau = sh.top_tau;
-      const uint32_t top_n = sh.top_n;
+      const float amin = sh.ac_min;
+      const bool order_ok = sh.order_ok != 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         beg[k] = static_cast<uint32_t>(sa[k].x);
@@ -941,17 +937,20 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         if (ts[k] >= 0 && tc[k] < wc) {
           ++n_expanded;
           n_arcs += cnt[k];
-          if (sb[k].x >= 0) {
+          if (order_ok && sb[k].x >= 0) {
             // an arc can only pass if ac < cutoff - cost - w <= slack (margin for fp rounding)
             const double slack = (cut_seed - tc[k]) - widen(__int_as_float(sb[k].y));
             const float sf = __double2float_ru(slack + 1e-6 * (fabs(cut_seed) + 1.0));
-            if (sf <= tau) {
-              uint32_t kk = 0;  // labels of the sorted list with ac < sf
-              for (uint32_t q = 0; q < top_n; ++q) kk += sh.top_ac[q] < sf;
-              if (2 * kk < cnt[k]) {
-                tab[k] = sb[k].x;
-                cnt[k] = kk;
-              }
+            // labels with ac < sf lie in buckets <= bucket(sf): a prefix of lab_order
+            const float d = (sf - amin) * 32.0f;
+            uint32_t kk = 0;
+            if (d >= 0.0f) {
+              const int b = d < static_cast<float>(kOrderBins) ? static_cast<int>(d) : kOrderBins;
+              kk = sh.bin_start[b + 1];
+            }
+            if (2 * kk < cnt[k]) {
+              tab[k] = sb[k].x;
+              cnt[k] = kk;
             }
           }
         }
@@ -1036,7 +1035,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const uint32_t b = t_beg[t];
               const uint32_t k = j - t_ex[t];
               if (b & kLookupFlag) {
-                const uint32_t lab = sh.top_lab[k];
+                const uint32_t lab = sh.lab_order[k];
                 lk[u] = __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
                 aa[u] = b & ~kLookupFlag;  // base; the offset is added in stage 2
               } else {
