@@ -191,6 +191,10 @@ __device__ __forceinline__ double widen(float f) {
   return static_cast<double>(f);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ HVal ld_hval(const HVal *p) {
   ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
   HVal r;
@@ -328,14 +332,12 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
 // newly claimed slot is appended to this frame's slot list and, when
 // `eps_queue` is given (the state has epsilon arcs), to that queue: the
 // closure only visits those.  Returns kNoIdx on overflow.
-__device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
-                                               int32_t state, uint32_t *eps_queue,
-                                               uint32_t *eps_queue_n) {
-  // groups of 4 consecutive states share a 128-byte line; groups are scattered
-  uint32_t h = ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
-               (static_cast<uint32_t>(state) & 3u);
+__device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneBuf &B,
+                                                    Shared &sh, int32_t state, uint32_t h,
+                                                    int32_t k, uint32_t *eps_queue,
+                                                    uint32_t *eps_queue_n) {
+  // `k` is the key already loaded from slot `h` (the first probe)
   for (uint32_t probe = 0; probe < P.hcap; ++probe) {
-    int32_t k = __ldcg(&B.table[h].key);
     if (k == state) return h;
     if (k == kEmptyKey) {
       k = atomicCAS(&B.table[h].key, kEmptyKey, state);
@@ -359,9 +361,23 @@ __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B
       }
     }
     h = (h + 1) & P.hmask;
+    k = __ldcg(&B.table[h].key);
   }
   atomicOr(&sh.status, kStatusHashOverflow);
   return kNoIdx;
+}
+
+__device__ __forceinline__ uint32_t table_hash(const Params &P, int32_t state) {
+  // groups of 4 consecutive states share a 128-byte line; groups are scattered
+  return ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
+         (static_cast<uint32_t>(state) & 3u);
+}
+
+__device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
+                                               int32_t state, uint32_t *eps_queue,
+                                               uint32_t *eps_queue_n) {
+  const uint32_t h = table_hash(P, state);
+  return table_slot_from(P, B, sh, state, h, __ldcg(&B.table[h].key), eps_queue, eps_queue_n);
 }
 
 // Emitting-phase recombination: keep the lexicographic minimum of (cost, arg).
@@ -723,17 +739,31 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
 }
 
 // Recombines one emitting arc that survived pruning at its destination state.
+// The key and the value of the first probed slot are loaded together (same
+// 32-byte sector): the usual case -- the state already has its slot -- then costs
+// one round trip before the 128-bit CAS instead of two.
 __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
                                            uint32_t a, unsigned long long nk, uint32_t tok_abs) {
   const int2 no = __ldg(P.e_no + a);
-  const bool has_eps = no.x < 0;
-  const uint32_t h = table_slot(P, B, sh, no.x & 0x7FFFFFFF, has_eps ? B.queue : nullptr,
-                                &sh.q_n[0]);
-  if (h == kNoIdx) return;
+  const int32_t state = no.x & 0x7FFFFFFF;
   HVal mine;
   mine.cost = nk;
   mine.arg = (static_cast<unsigned long long>(a) << 32) | tok_abs;
-  table_min(&B.table[h].val, mine);
+  const uint32_t h0 = table_hash(P, state);
+  const int32_t k0 = __ldcg(&B.table[h0].key);
+  HVal cur = ld_hval(&B.table[h0].val);  // same sector as the key: one round trip for both
+  uint32_t h = h0;
+  if (k0 != state) {
+    h = table_slot_from(P, B, sh, state, h0, k0, no.x < 0 ? B.queue : nullptr, &sh.q_n[0]);
+    if (h == kNoIdx) return;
+    // a freshly claimed slot holds the empty value; a slot found further along is re-read
+    if (h != h0 || k0 != kEmptyKey) cur = ld_hval(&B.table[h].val);
+  }
+  while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
+    HVal got = cas_hval(&B.table[h].val, cur, mine);
+    if (got.cost == cur.cost && got.arg == cur.arg) return;
+    cur = got;
+  }
 }
 
 constexpr int kWindows = 4;  // 32-arc windows a warp keeps in flight
@@ -1081,6 +1111,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const uint32_t tok_abs = base + tile0 + t_tok[t];
               const unsigned long long nk = dkey(nw[u]);
               const uint32_t e = atomicAdd(&sh.cand_n, 1u);
+              // (prefetching e_no[a] into L2 here was measured slower)
               if (e < P.ccap) {
                 __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
                                               static_cast<uint32_t>(nk >> 32), a, tok_abs));

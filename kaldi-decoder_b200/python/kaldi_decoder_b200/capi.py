@@ -15,7 +15,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
-LIB_PATH = os.path.join(LIB_DIR, "libkd_b200.so")
+# KD_B200_LIB selects another build of the same ABI (A/B experiments)
+LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(LIB_DIR, "libkd_b200.so")
 
 KD_OK = 0
 KD_MEM_HOST = 0
