@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--threads-per-lane", type=int, default=0)
     ap.add_argument("--hash-capacity", type=int, default=1 << 17)
     ap.add_argument("--arena-records", type=int, default=0)
-    ap.add_argument("--lanes-per-group", type=int, default=0)
+    ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--cpu-sample-utts", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -239,7 +239,7 @@ def main():
     dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes,
                            hash_capacity=args.hash_capacity, arena_records=args.arena_records,
                            threads_per_lane=args.threads_per_lane,
-                           lanes_per_group=args.lanes_per_group)
+                           chunk_frames=args.chunk_frames)
     # every rank decodes its own utterances (seed differs per rank): weak scaling
     logp = make_device_logprobs(g, lanes, T, args.seed + 7919 * rank, args.peak, dev)
     torch.cuda.synchronize()

@@ -66,7 +66,8 @@ typedef struct kd_decoder_config {
   int64_t arena_records;    /* per-lane backpointer-store records (sum over frames of
                                tokens alive at frame end), 20 bytes each               */
   int32_t threads_per_lane; /* 128/256/512/1024; default chosen from max_lanes         */
-  int32_t lanes_per_group;  /* host-memory advance: lanes per copy/compute stage       */
+  int32_t chunk_frames;     /* host-memory advance: frames per copy/search pipeline
+                               stage (default 128)                                     */
 } kd_decoder_config;
 
 /* Search counters, summed over the frames decoded since kd_decoder_init.  They
@@ -176,7 +177,7 @@ KD_API int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out);
 KD_API int kd_decoder_last_advance_info(kd_decoder *d, float *kernel_ms, int32_t *launches);
 
 /* info[0..5] = max_lanes, hash_capacity, arena_records, threads_per_lane,
- *              device bytes allocated, lanes_per_group */
+ *              device bytes allocated, chunk_frames */
 KD_API int kd_decoder_info(kd_decoder *d, int64_t info[6]);
 
 #ifdef __cplusplus

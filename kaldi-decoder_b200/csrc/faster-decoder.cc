@@ -38,7 +38,7 @@ kd_decoder_config ToC(const DeviceConfig &d, int32_t max_lanes) {
   c.hash_capacity = d.hash_capacity;
   c.arena_records = d.arena_records;
   c.threads_per_lane = d.threads_per_lane;
-  c.lanes_per_group = d.lanes_per_group;
+  c.chunk_frames = d.chunk_frames;
   if (const char *e = std::getenv("KD_B200_ARENA_RECORDS"))
     if (c.arena_records == 0) c.arena_records = std::atoll(e);
   if (const char *e = std::getenv("KD_B200_HASH_CAPACITY"))

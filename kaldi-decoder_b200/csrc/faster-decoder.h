@@ -67,7 +67,7 @@ struct DeviceConfig {
   int32_t hash_capacity = 0;
   int64_t arena_records = 0;
   int32_t threads_per_lane = 0;
-  int32_t lanes_per_group = 0;
+  int32_t chunk_frames = 0;
 };
 
 // The decoding graph resident on one GPU; immutable, shareable between decoders.

@@ -75,7 +75,7 @@ struct kd_decoder {
   uint32_t hcap = 0, lcap = 0, qcap = 0, ccap = 0;
   int64_t arena_cap = 0;
   int32_t threads = 0;  // 0 = auto per launch
-  int32_t lanes_per_group = 128;
+  int32_t chunk_frames = 128;
   size_t device_bytes = 0;
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
 
@@ -88,6 +88,9 @@ struct kd_decoder {
   uint32_t *queue = nullptr;
   uint4 *cand = nullptr;
   kd::AdvanceItem *d_items = nullptr;
+  int32_t *d_progress = nullptr;  // rows delivered by the copy stream (host-memory advance)
+  int32_t *h_progress = nullptr;  // pinned: one value per chunk
+  int32_t progress_cap = 0;
   int32_t *d_counters = nullptr;  // one per launch slot
   int32_t n_counters = 0;
   long long *d_out_off = nullptr;
@@ -216,6 +219,7 @@ const char *StatusText(int st) {
     return "backpointer arena overflow (raise kd_decoder_config.arena_records)";
   if (st & kd::kStatusQueueOverflow)
     return "epsilon worklist overflow (raise kd_decoder_config.hash_capacity)";
+  if (st & kd::kStatusInputStall) return "streamed log-probs did not arrive (copy stalled)";
   return "unknown device status";
 }
 
@@ -467,7 +471,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
     return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 192, 256 or 512");
   }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
-  d->lanes_per_group = c.lanes_per_group > 0 ? c.lanes_per_group : 128;
+  d->chunk_frames = c.chunk_frames > 0 ? c.chunk_frames : 128;
 
   const size_t L = static_cast<size_t>(d->max_lanes);
   const size_t table_bytes_per_lane =
@@ -489,11 +493,11 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
       (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
       (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
       (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) || (rc = DevAlloc(&d->d_items, L)) ||
-      (rc = DevAlloc(&d->d_out_off, L))) {
+      (rc = DevAlloc(&d->d_out_off, L)) || (rc = DevAlloc(&d->d_progress, static_cast<size_t>(1)))) {
     kd_decoder_destroy(d);
     return rc;
   }
-  d->n_counters = static_cast<int32_t>(L) + 8;
+  d->n_counters = static_cast<int32_t>(L) + 4096;
   if ((rc = DevAlloc(&d->d_counters, static_cast<size_t>(d->n_counters)))) {
     kd_decoder_destroy(d);
     return rc;
@@ -503,6 +507,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   KD_CUDA(cudaMemset(d->table, 0xFF, L * d->hcap * sizeof(kd::Entry)));
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
+
   KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
   for (int i = 0; i < kNumStreams; ++i) {
     KD_CUDA(cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking));
@@ -554,6 +559,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->queue);
   cudaFree(d->cand);
   cudaFree(d->d_items);
+  cudaFree(d->d_progress);
   cudaFree(d->d_counters);
   cudaFree(d->d_out_off);
   cudaFree(d->d_stage);
@@ -562,6 +568,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->d_gw);
   cudaFree(d->d_aw);
   if (d->h_items) cudaFreeHost(d->h_items);
+  if (d->h_progress) cudaFreeHost(d->h_progress);
   if (d->h_lanes) cudaFreeHost(d->h_lanes);
   if (d->h_out_off) cudaFreeHost(d->h_out_off);
   for (int i = 0; i < kNumStreams; ++i) {
@@ -703,8 +710,12 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
     KD_CUDA(cudaEventRecord(d->ev_end, s));
     KD_CUDA(cudaStreamSynchronize(s));
   } else {
-    // host matrices: stage group by group; copies and searches of different
-    // groups overlap on separate streams.
+    // Host matrices: ONE search launch; the copy stream delivers the frames in time
+    // chunks (all lanes, `chunk_frames` frames each) and publishes its progress in a
+    // device word the lanes poll when they run out of rows.  Lanes are latency bound
+    // and independent, so every lane should start as soon as its first frames are
+    // there and never wait for other lanes (relaunching per chunk costs the
+    // slowest-lane tail once per chunk: measured 189 vs 170 ms per step).
     if (stage_need > d->stage_floats) {
       KD_CUDA(cudaDeviceSynchronize());
       cudaFree(d->d_stage);
@@ -714,10 +725,11 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       if (rc) return rc;
       d->stage_floats = stage_need;
     }
-    const int32_t G = d->lanes_per_group;
-    const int32_t n_groups = (m + G - 1) / G;
+    const int32_t F = d->chunk_frames;
+    int32_t max_rows = 0;
     size_t pos = 0;
     for (int32_t i = 0; i < m; ++i) {
+      max_rows = std::max(max_rows, work[i].n_rows);
       d->h_items[i].lane = work[i].lane;
       d->h_items[i].rows = work[i].n_rows;
       d->h_items[i].offset = d->frames[work[i].lane];
@@ -725,36 +737,68 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       d->h_items[i].logp = d->d_stage + pos;
       pos += static_cast<size_t>(work[i].n_rows) * cols;
     }
-    cudaStream_t s0 = d->streams[0];
-    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
-                            cudaMemcpyHostToDevice, s0));
-    KD_CUDA(cudaMemsetAsync(d->d_counters, 0,
-                            sizeof(int32_t) * std::min(n_groups, d->n_counters), s0));
-    KD_CUDA(cudaEventRecord(d->ev_begin, s0));
-    for (int i = 1; i < kNumStreams; ++i)
-      KD_CUDA(cudaStreamWaitEvent(d->streams[i], d->ev_begin, 0));
-    const int threads = PickThreads(d, m);
-    for (int32_t gi = 0; gi < n_groups; ++gi) {
-      cudaStream_t s = d->streams[gi % kNumStreams];
-      const int32_t b = gi * G, e = std::min(m, b + G);
-      for (int32_t i = b; i < e; ++i) {
-        KD_CUDA(cudaMemcpyAsync(const_cast<float *>(d->h_items[i].logp), work[i].src,
-                                sizeof(float) * static_cast<size_t>(work[i].n_rows) * cols,
-                                cudaMemcpyHostToDevice, s));
+    const int32_t n_chunks = (max_rows + F - 1) / F;
+    if (n_chunks > d->progress_cap) {
+      KD_CUDA(cudaDeviceSynchronize());
+      if (d->h_progress) cudaFreeHost(d->h_progress);
+      d->h_progress = nullptr;
+      d->progress_cap = 0;
+      KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_progress),
+                             sizeof(int32_t) * (static_cast<size_t>(n_chunks) + 64)));
+      d->progress_cap = n_chunks + 64;
+    }
+    // one 2-D copy per chunk when the host matrices are equally long and equally spaced
+    bool uniform = m > 1;
+    ptrdiff_t src_stride = 0;
+    if (uniform) {
+      src_stride = work[1].src - work[0].src;
+      if (src_stride < static_cast<ptrdiff_t>(static_cast<size_t>(work[0].n_rows) * cols))
+        uniform = false;  // overlapping, unordered or identical matrices
+      for (int32_t i = 1; i < m && uniform; ++i) {
+        if (work[i].n_rows != work[0].n_rows) uniform = false;
+        if (work[i].src - work[i - 1].src != src_stride) uniform = false;
       }
-      kd::Params Pg = P;
-      Pg.items = d->d_items + b;
-      Pg.n_items = e - b;
-      Pg.work_counter = d->d_counters + (gi % d->n_counters);
-      rc = LaunchAdvance(d, Pg, e - b, threads, s);
-      if (rc) return rc;
     }
-    for (int i = 1; i < kNumStreams; ++i) {
-      KD_CUDA(cudaEventRecord(d->ev_stream[i], d->streams[i]));
-      KD_CUDA(cudaStreamWaitEvent(s0, d->ev_stream[i], 0));
+    cudaStream_t sc = d->streams[0], sx = d->streams[1];  // search, copy
+    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
+                            cudaMemcpyHostToDevice, sc));
+    KD_CUDA(cudaMemsetAsync(d->d_counters, 0, sizeof(int32_t), sc));
+    KD_CUDA(cudaMemsetAsync(d->d_progress, 0, sizeof(int32_t), sc));
+    KD_CUDA(cudaEventRecord(d->ev_begin, sc));
+    KD_CUDA(cudaStreamWaitEvent(sx, d->ev_begin, 0));  // copies start after the progress reset
+    P.n_items = m;
+    P.work_counter = d->d_counters;
+    P.progress = d->d_progress;
+    rc = LaunchAdvance(d, P, m, PickThreads(d, m), sc);
+    if (rc) return rc;
+    KD_CUDA(cudaEventRecord(d->ev_end, sc));
+    for (int32_t c = 0; c < n_chunks; ++c) {
+      const int32_t r0 = c * F;
+      if (uniform) {
+        const int32_t rows_c = std::min(F, work[0].n_rows - r0);
+        const size_t lane_floats = static_cast<size_t>(work[0].n_rows) * cols;
+        KD_CUDA(cudaMemcpy2DAsync(d->d_stage + static_cast<size_t>(r0) * cols,
+                                  lane_floats * sizeof(float),
+                                  work[0].src + static_cast<size_t>(r0) * cols,
+                                  static_cast<size_t>(src_stride) * sizeof(float),
+                                  static_cast<size_t>(rows_c) * cols * sizeof(float), m,
+                                  cudaMemcpyHostToDevice, sx));
+      } else {
+        for (int32_t i = 0; i < m; ++i) {
+          if (r0 >= work[i].n_rows) continue;
+          const int32_t rows_c = std::min(F, work[i].n_rows - r0);
+          KD_CUDA(cudaMemcpyAsync(
+              const_cast<float *>(d->h_items[i].logp) + static_cast<size_t>(r0) * cols,
+              work[i].src + static_cast<size_t>(r0) * cols,
+              sizeof(float) * static_cast<size_t>(rows_c) * cols, cudaMemcpyHostToDevice, sx));
+        }
+      }
+      d->h_progress[c] = std::min(max_rows, r0 + F);
+      KD_CUDA(cudaMemcpyAsync(d->d_progress, d->h_progress + c, sizeof(int32_t),
+                              cudaMemcpyHostToDevice, sx));
     }
-    KD_CUDA(cudaEventRecord(d->ev_end, s0));
-    KD_CUDA(cudaStreamSynchronize(s0));
+    KD_CUDA(cudaStreamSynchronize(sx));
+    KD_CUDA(cudaStreamSynchronize(sc));
   }
   KD_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev_begin, d->ev_end));
 
@@ -973,7 +1017,7 @@ int kd_decoder_info(kd_decoder *d, int64_t info[6]) {
   info[2] = d->arena_cap;
   info[3] = d->threads;
   info[4] = static_cast<int64_t>(d->device_bytes);
-  info[5] = d->lanes_per_group;
+  info[5] = d->chunk_frames;
   return KD_OK;
 }
 

@@ -48,6 +48,7 @@ namespace kd {
 constexpr int kStatusHashOverflow = 1;
 constexpr int kStatusArenaOverflow = 2;
 constexpr int kStatusQueueOverflow = 4;
+constexpr int kStatusInputStall = 8;  // streamed log-probs never arrived
 
 // In an arc field: "epsilon arc".  In a nextstate field: "state has epsilon arcs".
 constexpr uint32_t kEpsFlag = 0x80000000u;
@@ -149,6 +150,9 @@ struct Params {
   int32_t hshift;
   int32_t cols;
   int32_t row_in_smem;
+  // host-memory advance: rows [0, *progress) of every lane's staged matrix have
+  // arrived (written by the copy stream while the kernel runs); nullptr = all present
+  const int32_t *progress;
 };
 
 // ------------------------------------------------------------------ helpers
@@ -256,6 +260,7 @@ struct Shared {
   uint32_t acc_items;
   int status;
   int item;
+  int32_t rows_ready;
 };
 
 // min over the block of (v, idx); ties -> lowest idx.  All threads get it.
@@ -1198,10 +1203,31 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       sh.status = ls.status;
       sh.list_n = 0;
       sh.q_n[0] = 0;
+      sh.rows_ready = P.progress != nullptr ? 0 : 0x7FFFFFFF;
     }
     __syncthreads();
     while (ls.frames_decoded < it.target && sh.status == 0) {
       const int frame = ls.frames_decoded;
+      if (frame - it.offset >= sh.rows_ready) {
+        // the row has not been seen to arrive yet: poll the copy stream's progress word
+        __syncthreads();  // every thread has read rows_ready before thread 0 rewrites it
+        if (tid == 0) {
+          const volatile int32_t *pr = P.progress;
+          int32_t ready = *pr;
+          for (uint32_t spins = 0; ready <= frame - it.offset; ++spins) {
+            if (spins > (1u << 24)) {  // ~4 s: the copies are not coming
+              sh.status |= kStatusInputStall;
+              break;
+            }
+            __nanosleep(256);
+            ready = *pr;
+          }
+          __threadfence();
+          sh.rows_ready = ready;
+        }
+        __syncthreads();
+        if (sh.status != 0) break;
+      }
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
       const int n_in = ls.n_tok;
       double cstar;

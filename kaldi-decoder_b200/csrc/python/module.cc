@@ -200,7 +200,7 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def_readwrite("hash_capacity", &DeviceConfig::hash_capacity)
       .def_readwrite("arena_records", &DeviceConfig::arena_records)
       .def_readwrite("threads_per_lane", &DeviceConfig::threads_per_lane)
-      .def_readwrite("lanes_per_group", &DeviceConfig::lanes_per_group);
+      .def_readwrite("chunk_frames", &DeviceConfig::chunk_frames);
 
   py::class_<DeviceGraph, std::shared_ptr<DeviceGraph>>(m, "DeviceGraph")
       .def(py::init([](const fst::StdVectorFst &f, int32_t device) {

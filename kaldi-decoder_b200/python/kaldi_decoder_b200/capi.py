@@ -32,7 +32,7 @@ class KdOptions(C.Structure):
 class KdConfig(C.Structure):
     _fields_ = [("max_lanes", C.c_int32), ("hash_capacity", C.c_int32),
                 ("arena_records", C.c_int64), ("threads_per_lane", C.c_int32),
-                ("lanes_per_group", C.c_int32)]
+                ("chunk_frames", C.c_int32)]
 
 
 class KdStats(C.Structure):
@@ -179,10 +179,10 @@ class LaneDecoder:
 
     def __init__(self, graph: DeviceGraph, opts: KdOptions, max_lanes: int = 1,
                  hash_capacity: int = 0, arena_records: int = 0, threads_per_lane: int = 0,
-                 lanes_per_group: int = 0):
+                 chunk_frames: int = 0):
         self.graph = graph
         cfg = KdConfig(int(max_lanes), int(hash_capacity), int(arena_records),
-                       int(threads_per_lane), int(lanes_per_group))
+                       int(threads_per_lane), int(chunk_frames))
         h = C.c_void_p()
         _check(lib().kd_decoder_create(graph.h, C.byref(opts), C.byref(cfg), C.byref(h)))
         self.h = h
@@ -291,7 +291,7 @@ class LaneDecoder:
         v = np.zeros(6, np.int64)
         _check(lib().kd_decoder_info(self.h, v.ctypes.data))
         return dict(zip(("max_lanes", "hash_capacity", "arena_records", "threads_per_lane",
-                         "device_bytes", "lanes_per_group"), (int(x) for x in v)))
+                         "device_bytes", "chunk_frames"), (int(x) for x in v)))
 
 
 def merge_linear(path: RawPath):
