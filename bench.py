@@ -163,6 +163,12 @@ def make_device_logprobs(g, n_utts, T, seed, peak, device):
     return out
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of kd_advance_kernel from the committed
+# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt: 9.77 + 6.78 GB for a launch of
+# 1024 lanes x 100 frames of this workload), per lane-frame.  Only valid for config C3.
+NCU_DRAM_BYTES_PER_LANE_FRAME_C3 = (9.773089e9 + 6.778661e9) / (1024 * 100)
+
+
 def algorithmic_bytes(st: dict, cols: int) -> float:
     # SURVEY.md §8(d)
     return (16.0 * (st["emit_arcs"] + st["eps_arcs"]) + 16.0 * st["tokens_in"]
@@ -346,7 +352,11 @@ def main():
             "e2e": e2e,
             "gpu_launches": 4 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": None,
+                         "frac": achieved / peak_gbs,
+                         "traffic": (NCU_DRAM_BYTES_PER_LANE_FRAME_C3 * lanes * T
+                                     if args.config == "C3" and args.peak == 12.0 else None),
+                         "traffic_note": "DRAM bytes per launch scaled from the ncu capture in "
+                                         "profiles/r1_final_ncu_summary.txt (per lane-frame x lanes x frames)",
                          "kernel": "kd_advance_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "counters": st},

@@ -177,23 +177,29 @@ int PickThreads(const kd_decoder *d, int n_items) {
   return 512;
 }
 
-template <int THREADS, int MIN_BLOCKS>
-int LaunchAdvanceT(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
+template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
+int LaunchAdvanceR(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
   size_t smem = kd::advance_smem_fixed<THREADS>() + 16;
   if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(double);
   if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default limit too
-    KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS>,
+    KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(smem)));
   int per_sm = 1;
   KD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-      &per_sm, kd::kd_advance_kernel<THREADS, MIN_BLOCKS>, THREADS, smem));
+      &per_sm, kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM>, THREADS, smem));
   if (per_sm < 1) per_sm = 1;
   int grid = std::min(n_items, per_sm * d->num_sms);
-  kd::kd_advance_kernel<THREADS, MIN_BLOCKS><<<grid, THREADS, smem, s>>>(P);
+  kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM><<<grid, THREADS, smem, s>>>(P);
   KD_CUDA(cudaGetLastError());
   d->last_launches++;
   return KD_OK;
+}
+
+template <int THREADS, int MIN_BLOCKS>
+int LaunchAdvanceT(kd_decoder *d, const kd::Params &P, int n_items, cudaStream_t s) {
+  return P.row_in_smem ? LaunchAdvanceR<THREADS, MIN_BLOCKS, true>(d, P, n_items, s)
+                       : LaunchAdvanceR<THREADS, MIN_BLOCKS, false>(d, P, n_items, s);
 }
 
 int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,

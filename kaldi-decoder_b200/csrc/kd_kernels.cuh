@@ -1175,7 +1175,10 @@ __host__ __device__ constexpr size_t advance_smem_fixed() {
          THREADS * 4 * 2;                      // t_tok
 }
 
-template <int THREADS, int MIN_BLOCKS>
+// ROW_SMEM is a template parameter of the kernel (not a run-time branch): the
+// kernel is instruction-cache sensitive (7 lanes per SM run different phases of a
+// ~4500-instruction body), so only the variant in use is instantiated per launch.
+template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
   constexpr int TT = THREADS * 4;
   __shared__ Shared sh;
@@ -1230,13 +1233,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       }
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
       const int n_in = ls.n_tok;
-      double cstar;
-      if (P.row_in_smem)
-        cstar = lane_expand_emitting<THREADS, true>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
-                                                    t_beg, t_tab, t_tok);
-      else
-        cstar = lane_expand_emitting<THREADS, false>(P, B, sh, ls, row_g, s_row, t_cost, t_ex,
-                                                     t_beg, t_tab, t_tok);
+      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM>(P, B, sh, ls, row_g, s_row, t_cost,
+                                                                   t_ex, t_beg, t_tab, t_tok);
       // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
                                        cstar - 0.75 * static_cast<double>(P.beam));
