@@ -56,7 +56,8 @@ def parse_args():
     ap.add_argument("--peak", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--threads-per-lane", type=int, default=0)
-    ap.add_argument("--hash-capacity", type=int, default=1 << 17)
+    ap.add_argument("--hash-capacity", type=int, default=0,
+                    help="per-lane recombination table entries (default: per config)")
     ap.add_argument("--arena-records", type=int, default=0)
     ap.add_argument("--chunk-frames", type=int, default=0)
     ap.add_argument("--cpu-sample-utts", type=int, default=0)
@@ -67,6 +68,9 @@ def parse_args():
 
 
 CONFIG_LANES = {"C1": 64, "C2": 256, "C3": 1024, "C4": 1024}
+# tokens alive in one frame must stay below half of this (measured maxima: C1 500, C2 146k,
+# C3 49k, C4 142k tokens)
+CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 20, "C3": 1 << 18, "C4": 1 << 20}
 CONFIG_NAME = {
     "C1": "H-500 CTC topology, 64 utts x T=1000 x V=500, beam 20, max_active 7000",
     "C2": "HL 200k-word lexicon trie, 256 utts x T=1000 x V=500, beam 20, max_active 7000",
@@ -243,7 +247,8 @@ def main():
     V = int(g.lm["vocab"])
     dg = capi.DeviceGraph.from_graph(g, device=local_rank)
     dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes,
-                           hash_capacity=args.hash_capacity, arena_records=args.arena_records,
+                           hash_capacity=args.hash_capacity or CONFIG_HASH[args.config],
+                           arena_records=args.arena_records,
                            threads_per_lane=args.threads_per_lane,
                            chunk_frames=args.chunk_frames)
     # every rank decodes its own utterances (seed differs per rank): weak scaling
