@@ -1107,29 +1107,35 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
           // faster-decoder.cc:211 against the running cutoff
           if (tt[u] != kNoIdx && nw[u] < cut_d) adm |= 1u << u;
         }
-        if (adm) {
+        // Candidates are appended warp-aggregated: about a third of the looked-up arcs
+        // pass the filter, and one shared-memory atomic per candidate on the single
+        // counter serialised the whole CTA (the per-step cost was dominated by it).
 #pragma unroll
-          for (int u = 0; u < U; ++u) {
-            if (adm & (1u << u)) {
-              const uint32_t t = tt[u];
-              const uint32_t a = aa[u];
-              const uint32_t tok_abs = base + tile0 + t_tok[t];
-              const unsigned long long nk = dkey(nw[u]);
-              const uint32_t e = atomicAdd(&sh.cand_n, 1u);
-              // (prefetching e_no[a] into L2 here was measured slower)
-              if (e < P.ccap) {
-                __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
-                                              static_cast<uint32_t>(nk >> 32), a, tok_abs));
-              } else {
-                insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
-              }
-              if (nw[u] < my_min) {
-                my_min = nw[u];
-                // faster-decoder.cc:215-217
-                const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));
-                if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
-                  atomicMin(&sh.cut_fkey, fk);
-              }
+        for (int u = 0; u < U; ++u) {
+          const bool is_cand = (adm >> u) & 1u;
+          const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+          if (cmask == 0) continue;  // warp-uniform
+          uint32_t cbase = 0;
+          if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
+          cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+          if (is_cand) {
+            const uint32_t t = tt[u];
+            const uint32_t a = aa[u];
+            const uint32_t tok_abs = base + tile0 + t_tok[t];
+            const unsigned long long nk = dkey(nw[u]);
+            const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
+            if (e < P.ccap) {
+              __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
+                                            static_cast<uint32_t>(nk >> 32), a, tok_abs));
+            } else {
+              insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
+            }
+            if (nw[u] < my_min) {
+              my_min = nw[u];
+              // faster-decoder.cc:215-217
+              const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));
+              if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
+                atomicMin(&sh.cut_fkey, fk);
             }
           }
         }
