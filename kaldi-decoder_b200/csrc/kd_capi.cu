@@ -464,7 +464,19 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   cudaDeviceProp prop;
   KD_CUDA(cudaGetDeviceProperties(&prop, g->device));
   d->num_sms = prop.multiProcessorCount;
-  uint32_t hcap = c.hash_capacity > 0 ? static_cast<uint32_t>(c.hash_capacity) : (1u << 17);
+  // Default table size: the largest power of two that keeps all lanes' tables (and their
+  // slot lists, worklists, candidate buffers: 48 bytes per entry) within ~15% of the free
+  // device memory, between 2^15 and 2^22 entries.  A frame may hold capacity / 2 tokens.
+  uint32_t hcap;
+  if (c.hash_capacity > 0) {
+    hcap = static_cast<uint32_t>(c.hash_capacity);
+  } else {
+    size_t free_b = 0, total_b = 0;
+    KD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double per_lane = 0.15 * static_cast<double>(free_b) / d->max_lanes / 48.0;
+    hcap = 1u << 15;
+    while (hcap < (1u << 22) && 2.0 * hcap <= per_lane) hcap <<= 1;
+  }
   uint32_t p2 = 64;
   while (p2 < hcap && p2 < (1u << 30)) p2 <<= 1;
   d->hcap = p2;
