@@ -116,6 +116,7 @@ struct kd_decoder {
   cudaEvent_t ev_stream[kNumStreams] = {};
   float last_kernel_ms = 0.f;
   int32_t last_launches = 0;
+  int32_t last_blocks_per_sm = 0;
 };
 
 namespace {
@@ -180,7 +181,7 @@ int PickThreads(const kd_decoder *d, int n_items) {
 template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
 int LaunchAdvanceR(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
   size_t smem = kd::advance_smem_fixed<THREADS>() + 16;
-  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * sizeof(double);
+  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * (sizeof(float) + sizeof(uint16_t));
   if (smem > 32 * 1024)  // static shared memory counts against the 48 KB default limit too
     KD_CUDA(cudaFuncSetAttribute(kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -193,6 +194,7 @@ int LaunchAdvanceR(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
   kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM><<<grid, THREADS, smem, s>>>(P);
   KD_CUDA(cudaGetLastError());
   d->last_launches++;
+  d->last_blocks_per_sm = per_sm;
   return KD_OK;
 }
 
@@ -706,7 +708,7 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
 
   kd::Params P = MakeParams(d);
   P.cols = cols;
-  P.row_in_smem = (static_cast<size_t>(cols) * sizeof(double) <= 32768) ? 1 : 0;
+  P.row_in_smem = (static_cast<size_t>(cols) * 6 <= 49152) ? 1 : 0;
 
   if (mem_kind == KD_MEM_DEVICE) {
     for (int32_t i = 0; i < m; ++i) {

@@ -60,8 +60,9 @@ constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
 constexpr uint32_t kClassB = 0x80000000u;
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
-constexpr int kOrderBins = 1024;          // buckets of the per-frame label order (1/32 wide)
+constexpr int kOrderBins = 512;           // buckets of the per-frame label order (1/16 wide)
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
+constexpr int kTileTokens = 4;            // tokens per thread in one scan tile (6 was measured slower: less L1)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
 struct __align__(16) HVal {
@@ -253,8 +254,6 @@ struct Shared {
   uint32_t sel_bin, sel_k;
   // the frame's labels ordered by bucket of their acoustic cost (-log-prob - minimum):
   // labels with cost below a bound are lab_order[0 .. bin_start[bucket(bound) + 1])
-  uint16_t lab_order[kMaxOrderCols];
-  uint16_t bin_start[kOrderBins + 2];
   float ac_min;
   int order_ok;
   uint32_t acc_items;
@@ -805,11 +804,13 @@ constexpr int kWindows = 4;  // 32-arc windows a warp keeps in flight
 // new_weight < C* touch the table, so the table holds exactly the tokens.
 template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       LaneState &ls, const float *row_g, double *s_row,
+                                       LaneState &ls, const float *row_g, float *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
-                                       int32_t *t_tab, uint16_t *t_tok) {
+                                       int32_t *t_tab, uint16_t *t_tok, uint16_t *lab_order,
+                                       uint16_t *bin_start) {
   constexpr int U = kWindows;
-  constexpr int TT = THREADS * 4;
+  constexpr int KT = kTileTokens;
+  constexpr int TT = THREADS * KT;
   constexpr int NW = THREADS / 32;
   // 32-ary search over up to TT compacted tokens: strides 1024, 32, 1 (or 32, 1)
   constexpr uint32_t kSearchTop = TT > 1024 ? 1024u : 32u;
@@ -823,10 +824,10 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   const long long t_begin = clock64();
 
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29),
-  // already negated (faster-decoder.cc:209) and widened to fp64
+  // already negated (faster-decoder.cc:209); widened to fp64 where it is used.
+  // (Shared memory is kept small on purpose: what it does not take is L1.)
   if (ROW_SMEM) {
-    for (int i = tid; i < P.cols; i += THREADS)
-      s_row[i] = static_cast<double>(-__ldg(row_g + i));
+    for (int i = tid; i < P.cols; i += THREADS) s_row[i] = -__ldg(row_g + i);
   }
   if (tid == 0) {
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
@@ -838,21 +839,21 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &abf);
   const double ab = static_cast<double>(abf);
   __syncthreads();
-  // Order the frame's labels by acoustic cost (counting sort into 1/32-wide buckets
+  // Order the frame's labels by acoustic cost (counting sort into 1/16-wide buckets
   // above the minimum).  A token whose slack admits few labels looks those labels up
   // in its state's label table instead of scanning all its arcs.
   if (ROW_SMEM && P.cols <= kMaxOrderCols && P.labtab != nullptr) {
     uint32_t *hist = reinterpret_cast<uint32_t *>(t_cost);  // 2 * TT words, free until the scan
     static_assert(2 * TT >= kOrderBins, "tile too small to hold the label histogram");
     float amin = __int_as_float(0x7F800000);
-    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, static_cast<float>(s_row[i]));
+    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, s_row[i]);
     for (int b = tid; b < kOrderBins; b += THREADS) hist[b] = 0;
     double dmin;
     int dummy;
     block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
     amin = static_cast<float>(dmin);
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = (static_cast<float>(s_row[i]) - amin) * 32.0f;
+      const float d = (s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
       atomicAdd(&hist[b], 1u);
     }
@@ -878,23 +879,23 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       for (int k = 0; k < PER; ++k) {
         const int b = tid * PER + k;
         if (b < kOrderBins) {
-          sh.bin_start[b] = static_cast<uint16_t>(ex);
+          bin_start[b] = static_cast<uint16_t>(ex);
           hist[b] = ex;  // scatter cursor
           ex += loc[k];
         }
       }
       if (tid == 0) {
-        sh.bin_start[kOrderBins] = static_cast<uint16_t>(P.cols);
-        sh.bin_start[kOrderBins + 1] = static_cast<uint16_t>(P.cols);
+        bin_start[kOrderBins] = static_cast<uint16_t>(P.cols);
+        bin_start[kOrderBins + 1] = static_cast<uint16_t>(P.cols);
         sh.ac_min = amin;
         sh.order_ok = 1;
       }
     }
     __syncthreads();
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = (static_cast<float>(s_row[i]) - amin) * 32.0f;
+      const float d = (s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
-      sh.lab_order[atomicAdd(&hist[b], 1u)] = static_cast<uint16_t>(i + 1);
+      lab_order[atomicAdd(&hist[b], 1u)] = static_cast<uint16_t>(i + 1);
     }
     __syncthreads();
   } else {
@@ -907,7 +908,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     const int4 st = __ldg(P.st + 2 * static_cast<size_t>(state[ls.best_idx]));
     for (int a = tid; a < st.y; a += THREADS) {
       const int2 iw = __ldg(P.e_iw + st.x + a);
-      const double ac = ROW_SMEM ? s_row[iw.x - 1] : widen(-__ldg(row_g + iw.x - 1));
+      const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
       const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
       seed = fmin(seed, nw);
     }
@@ -934,14 +935,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
        tile0 = tile_end, tile_end = min(static_cast<uint32_t>(n), tile0 + TT)) {
     // tile setup: 4 consecutive tokens per thread -> compacted (cost, arc
     // range, arc prefix) of the tokens to expand
-    uint32_t cnt[4], beg[4];
-    int32_t tab[4];
-    double tc[4];
+    uint32_t cnt[KT], beg[KT];
+    int32_t tab[KT];
+    double tc[KT];
     {
-      int32_t ts[4];
+      int32_t ts[KT];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t i = tile0 + 4 * tid + k;
+      for (int k = 0; k < KT; ++k) {
+        const uint32_t i = tile0 + KT * tid + k;
         tc[k] = inf;
         ts[k] = -1;
         if (i < tile_end) {
@@ -950,9 +951,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         }
       }
 #pragma unroll
-      int4 sa[4], sb[4];
+      int4 sa[KT], sb[KT];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KT; ++k) {
         sa[k] = make_int4(0, 0, 0, 0);
         sb[k] = make_int4(-1, 0, 0, 0);
         if (ts[k] >= 0 && tc[k] < wc) {  // faster-decoder.cc:202
@@ -965,7 +966,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       const float amin = sh.ac_min;
       const bool order_ok = sh.order_ok != 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < KT; ++k) {
         beg[k] = static_cast<uint32_t>(sa[k].x);
         cnt[k] = static_cast<uint32_t>(sa[k].y);  // work items: arcs, or labels to look up
         tab[k] = -1;
@@ -977,11 +978,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
             const double slack = (cut_seed - tc[k]) - widen(__int_as_float(sb[k].y));
             const float sf = __double2float_ru(slack + 1e-6 * (fabs(cut_seed) + 1.0));
             // labels with ac < sf lie in buckets <= bucket(sf): a prefix of lab_order
-            const float d = (sf - amin) * 32.0f;
+            const float d = (sf - amin) * 16.0f;
             uint32_t kk = 0;
             if (d >= 0.0f) {
               const int b = d < static_cast<float>(kOrderBins) ? static_cast<int>(d) : kOrderBins;
-              kk = sh.bin_start[b + 1];
+              kk = bin_start[b + 1];
             }
             if (2 * kk < cnt[k]) {
               tab[k] = sb[k].x;
@@ -991,8 +992,12 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         }
       }
     }
-    const uint32_t my_arcs = cnt[0] + cnt[1] + cnt[2] + cnt[3];
-    const uint32_t my_toks = (cnt[0] != 0) + (cnt[1] != 0) + (cnt[2] != 0) + (cnt[3] != 0);
+    uint32_t my_arcs = 0, my_toks = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      my_arcs += cnt[k];
+      my_toks += cnt[k] != 0;
+    }
     uint32_t w_arcs, w_toks;
     uint32_t ex_arcs = warp_excl_scan(my_arcs, &w_arcs);
     uint32_t ex_toks = warp_excl_scan(my_toks, &w_toks);
@@ -1013,13 +1018,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       n_comp += t;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < KT; ++k) {
       if (cnt[k] != 0) {
         t_ex[ex_toks] = ex_arcs;
         t_beg[ex_toks] = beg[k] | (tab[k] >= 0 ? kLookupFlag : 0u);
         t_tab[ex_toks] = tab[k];
         t_cost[ex_toks] = tc[k];
-        t_tok[ex_toks] = static_cast<uint16_t>(4 * tid + k);
+        t_tok[ex_toks] = static_cast<uint16_t>(KT * tid + k);
         ex_arcs += cnt[k];
         ++ex_toks;
       }
@@ -1070,7 +1075,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const uint32_t b = t_beg[t];
               const uint32_t k = j - t_ex[t];
               if (b & kLookupFlag) {
-                const uint32_t lab = sh.lab_order[k];
+                const uint32_t lab = lab_order[k];
                 lk[u] = __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
                 aa[u] = b & ~kLookupFlag;  // base; the offset is added in stage 2
               } else {
@@ -1101,7 +1106,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         uint32_t adm = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const double ac = ROW_SMEM ? s_row[iw[u].x - 1] : widen(-__ldg(row_g + iw[u].x - 1));
+          const double ac = widen(ROW_SMEM ? s_row[iw[u].x - 1] : -__ldg(row_g + iw[u].x - 1));
           const double tcst = t_cost[min(tt[u], static_cast<uint32_t>(TT - 1))];
           nw[u] = (widen(__int_as_float(iw[u].y)) + tcst) + ac;
           // faster-decoder.cc:211 against the running cutoff
@@ -1175,10 +1180,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
 // Dynamic shared memory of kd_advance_kernel without the log-prob row, bytes.
 template <int THREADS>
 __host__ __device__ constexpr size_t advance_smem_fixed() {
-  return THREADS * 4 * (sizeof(double) + 4) +  // t_cost, t_beg
-         (THREADS * 4 + 4) * 4 +               // t_ex
-         THREADS * 4 * 4 +                     // t_tab
-         THREADS * 4 * 2;                      // t_tok
+  return THREADS * kTileTokens * (sizeof(double) + 4) +  // t_cost, t_beg
+         (THREADS * kTileTokens + 4) * 4 +               // t_ex
+         THREADS * kTileTokens * 4 +                     // t_tab
+         THREADS * kTileTokens * 2 +                     // t_tok
+         (kOrderBins + 2) * 2 + 12;                      // bin_start (+ pad to 16)
 }
 
 // ROW_SMEM is a template parameter of the kernel (not a run-time branch): the
@@ -1186,7 +1192,7 @@ __host__ __device__ constexpr size_t advance_smem_fixed() {
 // ~4500-instruction body), so only the variant in use is instantiated per launch.
 template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
-  constexpr int TT = THREADS * 4;
+  constexpr int TT = THREADS * kTileTokens;
   __shared__ Shared sh;
   __shared__ LaneState ls;
   __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
@@ -1197,7 +1203,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
   uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
   int32_t *t_tab = reinterpret_cast<int32_t *>(t_ex + TT + 4);
   uint16_t *t_tok = reinterpret_cast<uint16_t *>(t_tab + TT);
-  double *s_row = reinterpret_cast<double *>(t_tok + TT);  // TT * 2 bytes: 8-byte aligned
+  uint16_t *bin_start = t_tok + TT;                       // kOrderBins + 2 entries
+  float *s_row = reinterpret_cast<float *>(bin_start + kOrderBins + 8);  // 4-byte aligned
+  // the label order (one uint16 per column) follows the row
   const int tid = threadIdx.x;
 
   while (true) {
@@ -1239,8 +1247,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       }
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
       const int n_in = ls.n_tok;
-      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM>(P, B, sh, ls, row_g, s_row, t_cost,
-                                                                   t_ex, t_beg, t_tab, t_tok);
+      uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
+      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM>(
+          P, B, sh, ls, row_g, s_row, t_cost, t_ex, t_beg, t_tab, t_tok, lab_order, bin_start);
       // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
                                        cstar - 0.75 * static_cast<double>(P.beam));
