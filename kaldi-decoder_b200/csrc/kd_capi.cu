@@ -238,6 +238,12 @@ int CheckLanes(const kd_decoder *d, int32_t n, const int32_t *lanes) {
   for (int32_t i = 0; i < n; ++i)
     if (lanes[i] < 0 || lanes[i] >= d->max_lanes)
       return Fail(KD_ERR_INVALID, "lane id out of range");
+  // a lane may appear once per call (two CTAs must never own the same lane)
+  std::vector<char> seen(static_cast<size_t>(d->max_lanes), 0);
+  for (int32_t i = 0; i < n; ++i) {
+    if (seen[lanes[i]]) return Fail(KD_ERR_INVALID, "duplicate lane id in one call");
+    seen[lanes[i]] = 1;
+  }
   return KD_OK;
 }
 

@@ -122,6 +122,47 @@ def make_h(vocab: int = 500) -> Graph:
         lm={"kind": "h", "vocab": V})
 
 
+def make_random_fst(num_states: int = 200, num_arcs: int = 2000, vocab: int = 30,
+                    eps_frac: float = 0.15, seed: int = 0, neg_weight_frac: float = 0.1,
+                    dense_states: int = 4) -> Graph:
+    """Unstructured random FST for fuzzing: random weights (some negative), several arcs
+    with the same ilabel out of one state (non-deterministic), epsilon-input arcs only
+    from lower to higher state ids (no epsilon cycles), a few states with a large fan-out
+    of distinct labels (label-table candidates), random final states."""
+    rng = np.random.default_rng(np.random.PCG64(seed))
+    S, V = int(num_states), int(vocab)
+    src = rng.integers(0, S, size=num_arcs)
+    dst = rng.integers(0, S, size=num_arcs)
+    il = rng.integers(1, V + 1, size=num_arcs)
+    is_eps = rng.random(num_arcs) < eps_frac
+    # epsilon arcs go strictly upwards
+    lo, hi = np.minimum(src, dst), np.maximum(src, dst)
+    up = is_eps & (lo != hi)
+    src = np.where(up, lo, src)
+    dst = np.where(up, hi, dst)
+    is_eps = up
+    il = np.where(is_eps, 0, il)
+    ol = np.where(rng.random(num_arcs) < 0.3, rng.integers(1, 50, size=num_arcs), 0)
+    w = rng.uniform(0.0, 3.0, size=num_arcs).astype(np.float32)
+    neg = rng.random(num_arcs) < neg_weight_frac
+    w = np.where(neg & ~is_eps, -w * 0.3, w).astype(np.float32)
+    w = np.where(rng.random(num_arcs) < 0.2, np.float32(0.0), w).astype(np.float32)
+    # dense states: exactly one emitting arc per label (their random emitting arcs are dropped)
+    ds = rng.choice(S, size=min(dense_states, S), replace=False)
+    keep = ~(np.isin(src, ds) & (il != 0))
+    src, dst, il, ol, w = src[keep], dst[keep], il[keep], ol[keep], w[keep]
+    d_src = np.repeat(ds, V)
+    d_il = np.tile(np.arange(1, V + 1), ds.shape[0])
+    d_dst = rng.integers(0, S, size=d_src.shape[0])
+    d_w = rng.uniform(0.0, 2.0, size=d_src.shape[0]).astype(np.float32)
+    src = np.concatenate([src, d_src]); dst = np.concatenate([dst, d_dst])
+    il = np.concatenate([il, d_il]); ol = np.concatenate([ol, np.zeros(d_src.shape[0], np.int64)])
+    w = np.concatenate([w, d_w])
+    final = np.where(rng.random(S) < 0.2, rng.uniform(0, 2, size=S), np.inf).astype(np.float32)
+    return graph_from_arcs(S, 0, src, il, ol, w, dst, final, name=f"random-{S}-{seed}",
+                           lm={"kind": "h", "vocab": V})
+
+
 # ----------------------------------------------------------------- lexicon, LM
 
 def make_lexicon(n_words: int, vocab: int, rng: np.random.Generator,

@@ -60,3 +60,71 @@ def test_token_sets_match_canonical_oracle_every_frame(gname, oi):
                                                             "tokens_expanded", "emit_arcs")}
     for k, v in osum.items():
         assert st[k] == v, (k, st[k], v)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_random_fsts_every_frame(seed):
+    """Unstructured random graphs: negative weights, non-deterministic states, epsilon
+    chains, dense states (label tables) -- device token sets == canonical oracle, every frame."""
+    g = synth.make_random_fst(num_states=150 + 40 * seed, num_arcs=1500 + 300 * seed, vocab=25,
+                              eps_frac=0.1 + 0.03 * seed, seed=seed)
+    o = dict(beam=[6.0, 10.0, 14.0][seed % 3], max_active=[2**31 - 1, 60, 400][seed % 3],
+             min_active=[0, 5, 20][seed % 3])
+    kopts, ropts = capi.make_options(**o), kd_ref.Options(**o)
+    dg = capi.DeviceGraph.from_graph(g)
+    og = kd_oracle.OracleGraph(g)
+    n_lanes, T = 3, 60
+    dec = capi.LaneDecoder(dg, kopts, max_lanes=n_lanes, hash_capacity=1 << 14, arena_records=1 << 18)
+    rng = np.random.default_rng(seed)
+    mats = []
+    for u in range(n_lanes):
+        x = rng.standard_normal((T, 25)).astype(np.float32) * np.float32(1.5)
+        x[np.arange(T), rng.integers(0, 25, size=T)] += np.float32(5.0)
+        x -= np.log(np.exp(x).sum(axis=1, keepdims=True))
+        mats.append(x.astype(np.float32))
+    oracles = [kd_oracle.OracleDecoder(og, ropts, kd_oracle.CANONICAL) for _ in range(n_lanes)]
+    lanes = list(range(n_lanes))
+    dec.init(lanes)
+    for orc in oracles:
+        orc.init_decoding()
+    for f in range(T + 1):
+        for u in lanes:
+            gs, gc = sorted_tokens(*dec.tokens(u))
+            os_, oc = sorted_tokens(*oracles[u].tokens())
+            assert np.array_equal(gs, os_), (seed, u, f, len(gs), len(os_))
+            assert np.array_equal(gc, oc), (seed, u, f)
+        if f == T:
+            break
+        dec.advance(lanes, mats, max_num_frames=1)
+        for u in lanes:
+            oracles[u].advance_decoding(mats[u], 0, 1)
+    paths = dec.best_paths(lanes, True)
+    for u in lanes:
+        ob = oracles[u].get_best_path(True, raw=True)
+        assert paths[u].ok == ob.ok and paths[u].reached_final == oracles[u].reached_final()
+        if ob.ok:
+            assert rel_close(paths[u].total_cost, ob.total_cost, 1e-6)
+
+
+def test_wide_rows_take_the_global_memory_path():
+    """More columns than fit the shared-memory row staging: the row is gathered from global
+    memory (no label order); results must not change."""
+    g = small_graph("HL")
+    opts = dict(beam=14.0, max_active=500, min_active=20)
+    T, V, W = 50, 50, 9000
+    lp = synth.make_logprobs(g, T, seed=8, peak=6)
+    wide = np.full((T, W), -30.0, dtype=np.float32)
+    wide[:, :V] = lp
+    dg = capi.DeviceGraph.from_graph(g)
+    dec = capi.LaneDecoder(dg, capi.make_options(**opts), max_lanes=2, hash_capacity=1 << 14,
+                           arena_records=1 << 18)
+    dec.init([0, 1])
+    dec.advance([0], [lp])
+    dec.advance([1], [wide])
+    s0, c0 = sorted_tokens(*dec.tokens(0))
+    s1, c1 = sorted_tokens(*dec.tokens(1))
+    assert np.array_equal(s0, s1) and np.array_equal(c0, c1)
+    a, b = dec.best_paths([0, 1])
+    assert np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.acoustic, b.acoustic)
+    with pytest.raises(capi.KdError, match="duplicate lane"):
+        dec.init([0, 0])

@@ -72,3 +72,31 @@ def test_batch_entry_points_agree():
     for a, b in zip(rp, op):
         assert np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.acoustic, b.acoustic)
     assert stats["frames"] == 6 * 80 and per.shape[0] == 6
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_random_fsts_negative_weights_nondeterminism(seed):
+    """Unstructured random graphs (negative weights, duplicate ilabels per state, epsilon
+    chains): the restatement still equals the reference frame by frame."""
+    g = synth.make_random_fst(num_states=120 + 30 * seed, num_arcs=1200 + 200 * seed, vocab=20,
+                              eps_frac=0.1 + 0.04 * seed, seed=seed)
+    rg, og = kd_ref.RefGraph(g), kd_oracle.OracleGraph(g)
+    opts = kd_ref.Options(beam=[6.0, 10.0, 14.0][seed % 3], max_active=[2**31 - 1, 60, 400][seed % 3],
+                          min_active=[0, 5, 20][seed % 3])
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((70, 20)).astype(np.float32) * np.float32(1.5)
+    x[np.arange(70), rng.integers(0, 20, size=70)] += np.float32(4.0)
+    x = (x - np.log(np.exp(x).sum(axis=1, keepdims=True))).astype(np.float32)
+    r = kd_ref.RefDecoder(rg, opts)
+    o = kd_oracle.OracleDecoder(og, opts, kd_oracle.REFERENCE_ORDER)
+    r.init_decoding()
+    o.init_decoding()
+    for f in range(70):
+        r.advance_decoding(x, 0, 1)
+        o.advance_decoding(x, 0, 1)
+        rs, rc = r.tokens()
+        os_, oc = o.tokens()
+        assert np.array_equal(rs, os_) and np.array_equal(rc, oc), (seed, f)
+    a, b = r.get_best_path(), o.get_best_path()
+    assert a.ok == b.ok and np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.graph, b.graph)
+    assert np.array_equal(a.acoustic, b.acoustic) and np.array_equal(a.final, b.final)
