@@ -91,6 +91,7 @@ typedef struct kd_stats {
   int64_t candidates;      /* emitting arcs that passed the running-cutoff filter */
   int64_t arcs_evaluated;  /* arcs actually loaded: scanned, or found through a label
                               table; emit_arcs - this = arcs skipped as provably pruned */
+  int64_t cycles_scan;     /* part of cycles_expand before the exact cutoff       */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

@@ -87,6 +87,7 @@ struct kd_decoder {
   uint32_t *list = nullptr;
   uint32_t *queue = nullptr;
   uint4 *cand = nullptr;
+  uint4 *front = nullptr;
   kd::AdvanceItem *d_items = nullptr;
   int32_t *d_progress = nullptr;  // rows delivered by the copy stream (host-memory advance)
   int32_t *h_progress = nullptr;  // pinned: one value per chunk
@@ -160,6 +161,7 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.list = d->list;
   P.queue = d->queue;
   P.cand = d->cand;
+  P.front = d->front;
   P.ccap = d->ccap;
   P.hcap = d->hcap;
   P.hmask = d->hcap - 1;
@@ -518,7 +520,8 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   if ((rc = DevAlloc(&d->lanes, L)) || (rc = DevAlloc(&d->a_cost, L * A)) ||
       (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
       (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
-      (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) || (rc = DevAlloc(&d->d_items, L)) ||
+      (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) ||
+      (rc = DevAlloc(&d->front, L * kd::kFrontCap)) || (rc = DevAlloc(&d->d_items, L)) ||
       (rc = DevAlloc(&d->d_out_off, L)) || (rc = DevAlloc(&d->d_progress, static_cast<size_t>(1)))) {
     kd_decoder_destroy(d);
     return rc;
@@ -584,6 +587,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->list);
   cudaFree(d->queue);
   cudaFree(d->cand);
+  cudaFree(d->front);
   cudaFree(d->d_items);
   cudaFree(d->d_progress);
   cudaFree(d->d_counters);
@@ -987,15 +991,23 @@ int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *st
   rc = FetchLaneStates(d, 1, &lane);
   if (rc) return rc;
   const kd::LaneState &L = d->h_lanes[lane];
-  if (n) *n = L.n_tok;
-  if (L.n_tok == 0 || L.n_tok > cap) return KD_OK;
+  if (n) *n = L.n_live;
+  if (L.n_live == 0 || L.n_live > cap) return KD_OK;
   const size_t base = static_cast<size_t>(lane) * static_cast<size_t>(d->arena_cap) + L.tok_base;
-  if (states)
-    KD_CUDA(cudaMemcpy(states, d->a_state + base, sizeof(int32_t) * L.n_tok,
-                       cudaMemcpyDeviceToHost));
-  if (costs)
-    KD_CUDA(cudaMemcpy(costs, d->a_cost + base, sizeof(double) * L.n_tok,
-                       cudaMemcpyDeviceToHost));
+  // the block may hold holes (state -1): records that are not tokens are squeezed out here
+  std::vector<int32_t> st(static_cast<size_t>(L.n_tok));
+  std::vector<double> co(static_cast<size_t>(L.n_tok));
+  KD_CUDA(cudaMemcpy(st.data(), d->a_state + base, sizeof(int32_t) * L.n_tok,
+                     cudaMemcpyDeviceToHost));
+  KD_CUDA(cudaMemcpy(co.data(), d->a_cost + base, sizeof(double) * L.n_tok,
+                     cudaMemcpyDeviceToHost));
+  int64_t k = 0;
+  for (int32_t i = 0; i < L.n_tok && k < L.n_live; ++i) {
+    if (st[i] < 0) continue;
+    if (states) states[k] = st[i];
+    if (costs) costs[k] = co[i];
+    ++k;
+  }
   return KD_OK;
 }
 
@@ -1025,6 +1037,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->slots_claimed += L.st_claimed;
     out->candidates += L.st_cand;
     out->arcs_evaluated += L.st_items;
+    out->cycles_scan += L.cyc_scan;
   }
   return KD_OK;
 }

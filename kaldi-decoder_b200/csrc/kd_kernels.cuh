@@ -58,11 +58,14 @@ constexpr int32_t kEmptyKey = -1;
 constexpr unsigned long long kEmptyCost = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
-constexpr uint32_t kClassB = 0x80000000u;
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
 constexpr int kOrderBins = 512;           // buckets of the per-frame label order (1/16 wide)
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
-constexpr int kTileTokens = 4;            // tokens per thread in one scan tile (6 was measured slower: less L1)
+#ifndef KD_TILE_TOKENS
+#define KD_TILE_TOKENS 2
+#endif
+constexpr int kTileTokens = KD_TILE_TOKENS;            // tokens per thread in one scan tile
+constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
 struct __align__(16) HVal {
@@ -77,25 +80,27 @@ struct __align__(16) HVal {
 struct __align__(32) Entry {
   HVal val;       // 16-byte aligned: target of the 128-bit CAS
   int32_t key;    // state id, kEmptyKey when free
-  uint32_t idx;   // commit pass: index of the token in the next block
+  uint32_t idx;   // position in this frame's slot list = index of the token in the next block
   uint32_t pad[2];
 };
 
 // Everything the device keeps per lane between calls.
 struct __align__(16) LaneState {
-  int32_t n_tok;           // tokens alive (the reference's toks_ list length)
+  int32_t n_tok;           // records in the current token block (n_live tokens + dead records)
   int32_t frames_decoded;  // num_frames_decoded_; -1 before InitDecoding
   int32_t status;          // kStatus* bits; non-zero = lane unusable until init
   int32_t best_idx;        // index (in the current token block) of a best token
-  int32_t n_front;         // tokens at the front of the block that are close to the best
+  int32_t n_live;          // tokens alive (the reference's toks_ list length)
+  int32_t n_front;         // tokens below good_cut; the first kFrontCap of them are in the front list
   uint32_t tok_base;       // arena index of the current token block
   uint32_t arena_used;     // arena records in use
   double best_cost;        // min cost over the current tokens (+inf if none)
+  double good_cut;         // tokens below it are scanned first in the next frame
   // counters (kd_stats)
   long long st_frames, st_tokens_in, st_expanded, st_emit_arcs, st_eps_arcs,
       st_tokens_out, st_max_tokens, st_sweeps;
   // SM cycles spent per phase (clock64 of thread 0), for the phase breakdown
-  long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit;
+  long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit, cyc_scan;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
   long long st_items;    // arcs actually evaluated (scanned + looked up)
@@ -104,7 +109,6 @@ struct __align__(16) LaneState {
   uint32_t bp_best_tok;    // arena index
   long long bp_len;
   float bp_final_w;
-  int32_t pad0;
 };
 
 struct AdvanceItem {
@@ -147,6 +151,7 @@ struct Params {
   uint32_t *list;
   uint32_t *queue;  // 2 * qcap per lane
   uint4 *cand;      // ccap per lane: arcs that passed the running-cutoff filter
+  uint4 *front;     // kFrontCap per lane: {cost, state, number} of the tokens close to the best
   uint32_t hcap, hmask, lcap, qcap, ccap;
   int32_t hshift;
   int32_t cols;
@@ -248,8 +253,9 @@ struct Shared {
   uint32_t list_n;
   uint32_t cand_n;
   uint32_t q_n[2];
-  uint32_t out_n;   // commit: tokens numbered in the front ("good") class
-  uint32_t out_b;   // commit: tokens numbered in the back class
+  double wc;        // this frame's weight_cutoff
+  uint32_t n_dead;  // commit: slot-list entries that are not tokens
+  uint32_t n_front; // commit: tokens below good_cut
   uint32_t count;
   uint32_t sel_bin, sel_k;
   // the frame's labels ordered by bucket of their acoustic cost (-log-prob - minimum):
@@ -314,6 +320,7 @@ struct LaneBuf {
   uint32_t *list;
   uint32_t *queue;
   uint4 *cand;
+  uint4 *front;
 };
 
 __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
@@ -326,6 +333,7 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   b.list = P.list + L * P.lcap;
   b.queue = P.queue + L * 2 * P.qcap;
   b.cand = P.cand + L * P.ccap;
+  b.front = P.front + L * kFrontCap;
   return b;
 }
 
@@ -350,6 +358,7 @@ __device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneB
         const uint32_t pos = atomicAdd(&sh.list_n, 1u);
         if (pos < P.lcap) {
           B.list[pos] = h;
+          B.table[h].idx = pos;  // tokens are numbered in claim order
         } else {
           atomicOr(&sh.status, kStatusHashOverflow);
         }
@@ -455,11 +464,12 @@ __device__ float select_kth(const double *cost, int n, uint32_t k, Shared &sh) {
   return funkey(prefix);
 }
 
-// faster-decoder.cc:244-336.  n tokens, best = min cost.  All threads return
+// faster-decoder.cc:244-336.  n records holding n_live tokens (holes cost +inf, so they
+// sort behind every token), best = min cost.  All threads return
 // the same (weight_cutoff, adaptive_beam).
 template <int THREADS>
-__device__ void lane_cutoff(const Params &P, const double *cost, int n, double best, Shared &sh,
-                            double *weight_cutoff, float *adaptive_beam) {
+__device__ void lane_cutoff(const Params &P, const double *cost, int n, int n_live, double best,
+                            Shared &sh, double *weight_cutoff, float *adaptive_beam) {
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   if (P.max_active == 0x7FFFFFFF && P.min_active == 0) {
     *adaptive_beam = P.beam;
@@ -468,14 +478,14 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, double b
   }
   const double beam_cutoff = best + static_cast<double>(P.beam);
   double max_cut = inf, min_cut = inf;
-  if (n > P.max_active)
+  if (n_live > P.max_active)
     max_cut = static_cast<double>(select_kth<THREADS>(cost, n, P.max_active, sh));
   if (max_cut < beam_cutoff) {
     *adaptive_beam = static_cast<float>(max_cut - best + static_cast<double>(P.beam_delta));
     *weight_cutoff = max_cut;
     return;
   }
-  if (n > P.min_active) {
+  if (n_live > P.min_active) {
     if (P.min_active == 0) {
       min_cut = best;
     } else {
@@ -507,7 +517,7 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, double b
 // has epsilon arcs (flag in the arc's nextstate word).
 __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
                                             uint32_t dst_word, unsigned long long cost_key,
-                                            uint32_t arc, uint32_t src_slot,
+                                            uint32_t arc, uint32_t src_number,
                                             unsigned long long cstar_key, uint32_t *q_next,
                                             uint32_t *q_next_n) {
   const uint32_t h =
@@ -515,7 +525,7 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
   if (h == kNoIdx) return;
   HVal mine;
   mine.cost = cost_key;
-  mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_slot;
+  mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_number;
   HVal cur = ld_hval(&B.table[h].val);
   while (true) {
     const bool cur_is_eps = (cur.arg >> 63) != 0;
@@ -545,8 +555,8 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(v.cost < cstar_key || is_eps)) return;
-  const int32_t state = __ldcg(&B.table[slot].key);
-  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(state));
+  const int2 ki = __ldcg(reinterpret_cast<const int2 *>(&B.table[slot].key));  // {state, number}
+  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(ki.x));
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
   *eps_count += static_cast<uint32_t>(st.w);
@@ -554,8 +564,8 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
     const int4 arc = __ldg(P.n_arc + a);
     const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
-    eps_arrival(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a), slot,
-                cstar_key, q_next, q_next_n);
+    eps_arrival(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a),
+                static_cast<uint32_t>(ki.y), cstar_key, q_next, q_next_n);
   }
 }
 
@@ -565,21 +575,22 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
 // On entry queue 0 holds the slots, claimed during the emitting phase (or by
 // InitDecoding), whose states have epsilon arcs.
 //
-// The commit writes the tokens with cost < good_cut first: the next frame's
-// scan starts with them, so its running cutoff tightens early and few arcs
-// that the exact cutoff rejects become candidates.
+// good_cut is handed to the next frame's scan, which takes the tokens below it
+// first: its running cutoff tightens early and few arcs that the exact cutoff
+// rejects become candidates.
 template <int THREADS>
 __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
                                         LaneState &ls, double cstar, double good_cut) {
   const int tid = threadIdx.x;
   const unsigned long long cstar_key = dkey(cstar);
-  const unsigned long long good_key = dkey(good_cut);
+  // good_cut <= C*: every entry below it is a token
+  const unsigned long long good_key = dkey(fmin(good_cut, cstar));
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const long long t_begin = clock64();
   if (tid == 0) {
     sh.q_n[1] = 0;
-    sh.out_n = 0;
-    sh.out_b = 0;
+    sh.n_dead = 0;
+    sh.n_front = 0;
     sh.acc_eps = 0;
   }
   __syncthreads();
@@ -603,64 +614,24 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   }
   __syncthreads();
   const long long t_mid = clock64();
-  // ---- commit, pass 1: number the live entries (4 entries per thread in flight)
+  // ---- commit: one pass over the slot list.  Tokens are numbered in claim order
+  // (Entry::idx, written when the slot was claimed), so the predecessor number that
+  // an epsilon arrival carries is final and nothing has to be counted first.  A
+  // thread wipes (key, val) of its own entries after reading them.
   const uint32_t m = min(sh.list_n, P.lcap);
-  for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {  // uniform trip count: full-warp ballots
-    uint32_t h[4];
-    HVal v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const uint32_t p = p0 + u * THREADS + tid;
-      h[u] = p < m ? B.list[p] : kNoIdx;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      v[u].cost = kEmptyCost;
-      v[u].arg = kEmptyArg;
-      if (h[u] != kNoIdx) v[u] = ld_hval(&B.table[h[u]].val);
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const bool live =
-          v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
-      const bool good = live && v[u].cost < good_key;
-      // warp-aggregated numbering within each class: one shared-memory atomic per warp
-      const uint32_t mask_a = __ballot_sync(0xFFFFFFFFu, good);
-      const uint32_t mask_b = __ballot_sync(0xFFFFFFFFu, live && !good);
-      uint32_t base_a = 0, base_b = 0;
-      if ((tid & 31) == 0) {
-        if (mask_a) base_a = atomicAdd(&sh.out_n, __popc(mask_a));
-        if (mask_b) base_b = atomicAdd(&sh.out_b, __popc(mask_b));
-      }
-      base_a = __shfl_sync(0xFFFFFFFFu, base_a, 0);
-      base_b = __shfl_sync(0xFFFFFFFFu, base_b, 0);
-      if (h[u] != kNoIdx) {
-        const uint32_t below = (1u << (tid & 31)) - 1u;
-        uint32_t idx = kNoIdx;
-        if (good) idx = base_a + __popc(mask_a & below);
-        else if (live) idx = kClassB | (base_b + __popc(mask_b & below));
-        B.table[h[u]].idx = idx;
-      }
-    }
-  }
-  __syncthreads();
-  const uint32_t n_front = sh.out_n;
-  const uint32_t n_new = n_front + sh.out_b;
   const uint32_t new_base = ls.arena_used;
-  if (static_cast<long long>(new_base) + n_new > P.arena_cap) {
+  if (static_cast<long long>(new_base) + m > P.arena_cap) {
     if (tid == 0) sh.status |= kStatusArenaOverflow;
   }
   __syncthreads();
   const bool write_ok = (sh.status & kStatusArenaOverflow) == 0;
-  // ---- commit, pass 2: write the token block and wipe the table.  A thread
-  // wipes (key, val) of its own entries after reading them; other threads
-  // read nothing but `idx` of foreign entries, which is never wiped.
   double my_min = inf;
   int my_arg = -1;
+  uint32_t dead = 0;
   for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {
     uint32_t h[4];
     HVal v[4];
-    int4 meta[4];  // {key, idx, pad, pad}
+    int32_t key[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint32_t p = p0 + u * THREADS + tid;
@@ -670,36 +641,49 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     for (int u = 0; u < 4; ++u) {
       v[u].cost = kEmptyCost;
       v[u].arg = kEmptyArg;
-      meta[u] = make_int4(kEmptyKey, static_cast<int>(kNoIdx), 0, 0);
+      key[u] = kEmptyKey;
       if (h[u] != kNoIdx) {
         v[u] = ld_hval(&B.table[h[u]].val);
-        meta[u] = __ldcg(reinterpret_cast<const int4 *>(&B.table[h[u]].key));
+        key[u] = __ldcg(&B.table[h[u]].key);
       }
     }
-    uint32_t prev_idx[4];
+    // the tokens close to the best also go to the front list (warp-aggregated append)
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      prev_idx[u] = 0;
-      if (h[u] != kNoIdx && static_cast<uint32_t>(meta[u].y) != kNoIdx && (v[u].arg >> 63) != 0) {
-        const uint32_t pi = __ldcg(&B.table[static_cast<uint32_t>(v[u].arg)].idx);
-        prev_idx[u] = (pi & kClassB) ? n_front + (pi & ~kClassB) : pi;
+      const bool good = v[u].cost < good_key;  // an empty value compares above every key
+      const uint32_t gmask = __ballot_sync(0xFFFFFFFFu, good);
+      if (gmask == 0) continue;  // warp-uniform
+      uint32_t gbase = 0;
+      if ((tid & 31) == 0) gbase = atomicAdd(&sh.n_front, __popc(gmask));
+      gbase = __shfl_sync(0xFFFFFFFFu, gbase, 0);
+      if (good) {
+        const uint32_t pos = gbase + __popc(gmask & ((1u << (tid & 31)) - 1u));
+        if (pos < static_cast<uint32_t>(kFrontCap))
+          B.front[pos] = make_uint4(static_cast<uint32_t>(v[u].cost),
+                                    static_cast<uint32_t>(v[u].cost >> 32),
+                                    static_cast<uint32_t>(key[u]), p0 + u * THREADS + tid);
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (h[u] == kNoIdx) continue;
-      uint32_t idx = static_cast<uint32_t>(meta[u].y);
-      if (idx != kNoIdx && (idx & kClassB)) idx = n_front + (idx & ~kClassB);
-      if (idx != kNoIdx && write_ok) {
+      const uint32_t idx = p0 + u * THREADS + tid;
+      // Not a token: an arrival recombined while the candidate buffer was full (against
+      // the running cutoff) that the exact cutoff rejects.  Its record stays in the
+      // block as a hole (state -1, cost +inf) that every reader skips.
+      const bool live =
+          v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
+      if (!live) ++dead;
+      if (write_ok) {
         const uint32_t arc = static_cast<uint32_t>(v[u].arg >> 32);
         uint32_t prev = static_cast<uint32_t>(v[u].arg);
-        if (arc & kEpsFlag) prev = new_base + prev_idx[u];
-        const double c = dunkey(v[u].cost);
+        if (arc & kEpsFlag) prev += new_base;  // predecessor is a token of this block
+        const double c = live ? dunkey(v[u].cost) : inf;
         // written once, read once next frame (cost, state) or at traceback (link)
         __stcs(B.a_cost + new_base + idx, c);
         __stcs(B.a_link + new_base + idx, (static_cast<unsigned long long>(arc) << 32) | prev);
-        __stcs(B.a_state + new_base + idx, meta[u].x);
-        if (c < my_min) {
+        __stcs(B.a_state + new_base + idx, live ? key[u] : -1);
+        if (live && c < my_min) {
           my_min = c;
           my_arg = static_cast<int>(idx);
         }
@@ -717,17 +701,22 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   // accumulate counters
   eps_count = __reduce_add_sync(0xFFFFFFFFu, eps_count);
   if ((tid & 31) == 0 && eps_count) atomicAdd(&sh.acc_eps, eps_count);
+  dead = __reduce_add_sync(0xFFFFFFFFu, dead);
+  if ((tid & 31) == 0 && dead) atomicAdd(&sh.n_dead, dead);
   __syncthreads();
   if (tid == 0) {
     if (write_ok) {
       ls.tok_base = new_base;
-      ls.n_tok = static_cast<int32_t>(n_new);
-      ls.arena_used = new_base + n_new;
+      ls.n_tok = static_cast<int32_t>(m);
+      ls.n_live = static_cast<int32_t>(m - sh.n_dead);
+      ls.arena_used = new_base + m;
       ls.best_cost = bmin;
       ls.best_idx = barg;
-      ls.n_front = static_cast<int32_t>(n_front);
+      ls.good_cut = fmin(good_cut, cstar);
+      ls.n_front = static_cast<int32_t>(sh.n_front);
     } else {
       ls.n_tok = 0;
+      ls.n_live = 0;
       ls.best_cost = inf;
       ls.best_idx = -1;
     }
@@ -806,7 +795,7 @@ template <int THREADS, bool ROW_SMEM>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
                                        LaneState &ls, const float *row_g, float *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
-                                       int32_t *t_tab, uint16_t *t_tok, uint16_t *lab_order,
+                                       int32_t *t_tab, uint32_t *t_tok, uint16_t *lab_order,
                                        uint16_t *bin_start) {
   constexpr int U = kWindows;
   constexpr int KT = kTileTokens;
@@ -836,15 +825,17 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   }
   double wc;
   float abf;
-  lane_cutoff<THREADS>(P, cost, n, ls.best_cost, sh, &wc, &abf);
+  lane_cutoff<THREADS>(P, cost, n, ls.n_live, ls.best_cost, sh, &wc, &abf);
   const double ab = static_cast<double>(abf);
+  if (tid == 0) sh.wc = wc;
   __syncthreads();
   // Order the frame's labels by acoustic cost (counting sort into 1/16-wide buckets
   // above the minimum).  A token whose slack admits few labels looks those labels up
   // in its state's label table instead of scanning all its arcs.
   if (ROW_SMEM && P.cols <= kMaxOrderCols && P.labtab != nullptr) {
-    uint32_t *hist = reinterpret_cast<uint32_t *>(t_cost);  // 2 * TT words, free until the scan
-    static_assert(2 * TT >= kOrderBins, "tile too small to hold the label histogram");
+    // the tile arrays (t_cost .. t_tok, contiguous, 6 * TT words) are free until the scan
+    uint32_t *hist = reinterpret_cast<uint32_t *>(t_cost);
+    static_assert(6 * TT >= kOrderBins, "tile arrays too small to hold the label histogram");
     float amin = __int_as_float(0x7F800000);
     for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, s_row[i]);
     for (int b = tid; b < kOrderBins; b += THREADS) hist[b] = 0;
@@ -923,21 +914,33 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   if (tid == 0) sh.t_mark = clock64();
 
   // ---------------------------------------------------------------- scan
-  uint32_t n_expanded = 0, n_arcs = 0;
   double my_min = inf;
-  // The first tile is the front class of the block (tokens close to the best,
-  // see the commit): scanning it first makes the running cutoff tight before the
-  // bulk of the tokens is classified (scan vs label lookup) and filtered.
-  const uint32_t first_tile =
-      ls.n_front > 0 ? min(static_cast<uint32_t>(ls.n_front), static_cast<uint32_t>(TT)) : TT;
-  for (uint32_t tile0 = 0, tile_end = min(static_cast<uint32_t>(n), first_tile);
-       tile0 < static_cast<uint32_t>(n);
-       tile0 = tile_end, tile_end = min(static_cast<uint32_t>(n), tile0 + TT)) {
-    // tile setup: 4 consecutive tokens per thread -> compacted (cost, arc
-    // range, arc prefix) of the tokens to expand
-    uint32_t cnt[KT], beg[KT];
+  // Two passes over the token block.  Pass 0 takes the tokens close to the best
+  // (cost < good_cut, fixed by the previous commit): scanning them first makes the
+  // running cutoff tight before the bulk of the tokens is classified (scan vs label
+  // lookup) and filtered in pass 1.  Within a pass the tokens are read a chunk
+  // (kTileTokens per thread) at a time; the ones to expand are compacted into the tile
+  // arrays and worked off before the next chunk is classified.  Small chunks win:
+  // later chunks are classified against a tighter cutoff, and the tile arrays take
+  // little shared memory away from L1 (measured: 2 per thread beats 1, 3 and 4).
+  // (Loop state is kept in shared memory where it can be: the item loop below needs
+  // every register it can get.)
+  static_assert(TT <= kFrontCap, "front list smaller than a scan tile");
+  for (int pass = 0; pass < 2; ++pass) {
+    // pass 0 reads the front list the commit wrote, unless it overflowed (then it filters the block)
+    const bool front_list =
+        pass == 0 && static_cast<uint32_t>(ls.n_front) <= static_cast<uint32_t>(kFrontCap);
+    const uint32_t un = static_cast<uint32_t>(front_list ? ls.n_front : ls.n_tok);
+    for (uint32_t tile0 = 0; tile0 < un; tile0 += TT) {
+    const double wcut = sh.wc;
+    const double good = fmin(ls.good_cut, wcut);
+    const uint32_t tile_end = min(un, tile0 + TT);
+    // chunk setup: 4 consecutive tokens per thread -> (cost, arc range or label
+    // count) of the tokens to expand
+    uint32_t cnt[KT], beg[KT], ti[KT];
     int32_t tab[KT];
     double tc[KT];
+    uint32_t ch_expanded = 0, ch_arcs = 0;  // this chunk's share of the counters
     {
       int32_t ts[KT];
 #pragma unroll
@@ -945,18 +948,27 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         const uint32_t i = tile0 + KT * tid + k;
         tc[k] = inf;
         ts[k] = -1;
+        ti[k] = i;
         if (i < tile_end) {
-          tc[k] = __ldcs(cost + i);
-          ts[k] = __ldcs(state + i);
+          if (front_list) {
+            const uint4 rec = __ldcs(B.front + i);
+            tc[k] = dunkey((static_cast<unsigned long long>(rec.y) << 32) | rec.x);
+            ts[k] = static_cast<int32_t>(rec.z);
+            ti[k] = rec.w;
+          } else {
+            tc[k] = __ldcs(cost + i);
+            ts[k] = __ldcs(state + i);
+          }
         }
+        // faster-decoder.cc:202, split over the two passes (a hole has state -1, cost +inf)
+        if (!(pass == 0 ? tc[k] < good : (tc[k] >= good && tc[k] < wcut))) ts[k] = -1;
       }
-#pragma unroll
       int4 sa[KT], sb[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) {
         sa[k] = make_int4(0, 0, 0, 0);
         sb[k] = make_int4(-1, 0, 0, 0);
-        if (ts[k] >= 0 && tc[k] < wc) {  // faster-decoder.cc:202
+        if (ts[k] >= 0) {
           sa[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]));
           sb[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]) + 1);
         }
@@ -970,9 +982,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         beg[k] = static_cast<uint32_t>(sa[k].x);
         cnt[k] = static_cast<uint32_t>(sa[k].y);  // work items: arcs, or labels to look up
         tab[k] = -1;
-        if (ts[k] >= 0 && tc[k] < wc) {
-          ++n_expanded;
-          n_arcs += cnt[k];
+        if (ts[k] >= 0) {
+          ++ch_expanded;
+          ch_arcs += cnt[k];
           if (order_ok && sb[k].x >= 0) {
             // an arc can only pass if ac < cutoff - cost - w <= slack (margin for fp rounding)
             const double slack = (cut_seed - tc[k]) - widen(__int_as_float(sb[k].y));
@@ -984,11 +996,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const int b = d < static_cast<float>(kOrderBins) ? static_cast<int>(d) : kOrderBins;
               kk = bin_start[b + 1];
             }
-            if (2 * kk < cnt[k]) {
+            if (2 * kk < static_cast<uint32_t>(sa[k].y)) {
               tab[k] = sb[k].x;
               cnt[k] = kk;
             }
           }
+        } else {
+          cnt[k] = 0;
         }
       }
     }
@@ -1006,7 +1020,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       sh.warp_sums[16 + warp] = w_toks;
     }
     __syncthreads();
-    uint32_t n_flat = 0, n_comp = 0;
+    uint32_t n_flat = 0, n_comp = 0;  // work items / tokens in the tile (uniform)
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
       const uint32_t a = sh.warp_sums[w], t = sh.warp_sums[16 + w];
@@ -1024,20 +1038,24 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         t_beg[ex_toks] = beg[k] | (tab[k] >= 0 ? kLookupFlag : 0u);
         t_tab[ex_toks] = tab[k];
         t_cost[ex_toks] = tc[k];
-        t_tok[ex_toks] = static_cast<uint16_t>(KT * tid + k);
+        t_tok[ex_toks] = ti[k];
         ex_arcs += cnt[k];
         ++ex_toks;
       }
+    }
+    ch_expanded = __reduce_add_sync(0xFFFFFFFFu, ch_expanded);
+    ch_arcs = __reduce_add_sync(0xFFFFFFFFu, ch_arcs);
+    if (lane == 0 && ch_expanded) {
+      atomicAdd(&sh.acc_expanded, ch_expanded);
+      atomicAdd(&sh.acc_emit, ch_arcs);
     }
     if (tid == 0) {
       t_ex[n_comp] = n_flat;
       sh.acc_items += n_flat;
     }
     __syncthreads();
-    // flat arc loop: steps of 32 * U arcs are dealt round-robin to the warps, so
-    // all warps start at the front of the flat space, where the commit put the
-    // tokens most likely to produce the frame's best arcs: the running cutoff
-    // is tight after the first round.
+    // flat item loop: steps of 32 * U items are dealt round-robin to the warps, so
+    // all warps start at the front of the flat space.
     {
       const uint32_t jw1 = n_flat;
 #pragma unroll 1
@@ -1126,7 +1144,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
           if (is_cand) {
             const uint32_t t = tt[u];
             const uint32_t a = aa[u];
-            const uint32_t tok_abs = base + tile0 + t_tok[t];
+            const uint32_t tok_abs = base + t_tok[t];
             const unsigned long long nk = dkey(nw[u]);
             const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
             if (e < P.ccap) {
@@ -1146,12 +1164,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         }
       }
     }
-    __syncthreads();  // the tile arrays are rewritten by the next tile
+    // every warp's items count before the next chunk is classified (tighter cutoff)
+    __syncthreads();
+    }
   }
-  n_expanded = __reduce_add_sync(0xFFFFFFFFu, n_expanded);
-  n_arcs = __reduce_add_sync(0xFFFFFFFFu, n_arcs);
-  if (lane == 0 && n_expanded) atomicAdd(&sh.acc_expanded, n_expanded);
-  if (lane == 0 && n_arcs) atomicAdd(&sh.acc_emit, n_arcs);
+  const long long t_scan_end = clock64();
   // ---------------------------------------------------------------- exact cutoff
   double bmin;
   int dummy2;
@@ -1171,6 +1188,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     const long long t_end = clock64();
     ls.cyc_cutoff += sh.t_mark - t_begin;
     ls.cyc_expand += t_end - sh.t_mark;
+    ls.cyc_scan += t_scan_end - sh.t_mark;
   }
   return cstar;
 }
@@ -1183,7 +1201,7 @@ __host__ __device__ constexpr size_t advance_smem_fixed() {
   return THREADS * kTileTokens * (sizeof(double) + 4) +  // t_cost, t_beg
          (THREADS * kTileTokens + 4) * 4 +               // t_ex
          THREADS * kTileTokens * 4 +                     // t_tab
-         THREADS * kTileTokens * 2 +                     // t_tok
+         THREADS * kTileTokens * 4 +                     // t_tok
          (kOrderBins + 2) * 2 + 12;                      // bin_start (+ pad to 16)
 }
 
@@ -1202,8 +1220,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
   uint32_t *t_beg = reinterpret_cast<uint32_t *>(t_cost + TT);
   uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
   int32_t *t_tab = reinterpret_cast<int32_t *>(t_ex + TT + 4);
-  uint16_t *t_tok = reinterpret_cast<uint16_t *>(t_tab + TT);
-  uint16_t *bin_start = t_tok + TT;                       // kOrderBins + 2 entries
+  uint32_t *t_tok = reinterpret_cast<uint32_t *>(t_tab + TT);
+  uint16_t *bin_start = reinterpret_cast<uint16_t *>(t_tok + TT);  // kOrderBins + 2 entries
   float *s_row = reinterpret_cast<float *>(bin_start + kOrderBins + 8);  // 4-byte aligned
   // the label order (one uint16 per column) follows the row
   const int tid = threadIdx.x;
@@ -1246,7 +1264,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
         if (sh.status != 0) break;
       }
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
-      const int n_in = ls.n_tok;
+      const int n_in = ls.n_live;
       uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
       const double cstar = lane_expand_emitting<THREADS, ROW_SMEM>(
           P, B, sh, ls, row_g, s_row, t_cost, t_ex, t_beg, t_tab, t_tok, lab_order, bin_start);
@@ -1257,11 +1275,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
         ls.frames_decoded = frame + 1;
         ls.st_frames += 1;
         ls.st_tokens_in += n_in;
-        ls.st_tokens_out += ls.n_tok;
+        ls.st_tokens_out += ls.n_live;
         ls.st_emit_arcs += sh.acc_emit;
         ls.st_expanded += sh.acc_expanded;
         ls.st_items += sh.acc_items;
-        if (ls.n_tok > ls.st_max_tokens) ls.st_max_tokens = ls.n_tok;
+        if (ls.n_live > ls.st_max_tokens) ls.st_max_tokens = ls.n_live;
       }
       __syncthreads();
     }
@@ -1338,7 +1356,9 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
   __syncthreads();
   int any = 0;
   for (int i = tid; i < n; i += THREADS) {
-    float f = __ldg(P.fin + B.a_state[base + i]);
+    const int s = B.a_state[base + i];
+    if (s < 0) continue;  // a hole, not a token
+    float f = __ldg(P.fin + s);
     if (B.a_cost[base + i] != inf && f != __int_as_float(0x7F800000)) any = 1;
   }
   if (any) atomicOr(&s_any_final, 1);
@@ -1348,6 +1368,7 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
   int bs = -1;  // state id is the tie-break key; token index recovered below
   for (int i = tid; i < n; i += THREADS) {
     int s = B.a_state[base + i];
+    if (s < 0) continue;
     double c = B.a_cost[base + i];
     double v = is_final ? c + static_cast<double>(__ldg(P.fin + s)) : c;
     bool take = is_final ? (v != inf) : true;

@@ -106,6 +106,64 @@ def test_fuzz_random_fsts_every_frame(seed):
             assert rel_close(paths[u].total_cost, ob.total_cost, 1e-6)
 
 
+def _every_frame(g, o, mats, **dec_kw):
+    kopts, ropts = capi.make_options(**o), kd_ref.Options(**o)
+    dg = capi.DeviceGraph.from_graph(g)
+    og = kd_oracle.OracleGraph(g)
+    lanes = list(range(len(mats)))
+    dec = capi.LaneDecoder(dg, kopts, max_lanes=len(mats), **dec_kw)
+    oracles = [kd_oracle.OracleDecoder(og, ropts, kd_oracle.CANONICAL) for _ in lanes]
+    dec.init(lanes)
+    for orc in oracles:
+        orc.init_decoding()
+    peak_tokens = 0
+    for f in range(mats[0].shape[0]):
+        dec.advance(lanes, mats, max_num_frames=1)
+        for u in lanes:
+            oracles[u].advance_decoding(mats[u], 0, 1)
+            gs, gc = sorted_tokens(*dec.tokens(u))
+            os_, oc = sorted_tokens(*oracles[u].tokens())
+            assert np.array_equal(gs, os_), (u, f, len(gs), len(os_))
+            assert np.array_equal(gc, oc), (u, f)
+            peak_tokens = max(peak_tokens, len(gs))
+    paths = dec.best_paths(lanes, True)
+    for u in lanes:
+        ob = oracles[u].get_best_path(True, raw=True)
+        assert paths[u].ok == ob.ok and paths[u].reached_final == oracles[u].reached_final()
+        if ob.ok:
+            assert rel_close(paths[u].total_cost, ob.total_cost, 1e-6)
+    return dec, peak_tokens
+
+
+def test_full_candidate_buffer_leaves_holes_not_tokens():
+    """A candidate buffer (hash_capacity / 4 records) far smaller than a frame's candidates:
+    the overflow is recombined against the running cutoff, and what the exact cutoff then
+    rejects must not show up as tokens (nor in counts that feed GetCutoff)."""
+    g = small_graph("H")
+    T = 40
+    mats = [synth.make_logprobs(g, T, seed=900 + u, peak=2) for u in range(3)]
+    for o in (dict(beam=9.0, max_active=2**31 - 1, min_active=0),
+              dict(beam=12.0, max_active=25, min_active=10)):
+        dec, _ = _every_frame(g, o, mats, hash_capacity=256, arena_records=1 << 16)
+        st = dec.stats()
+        assert st["candidates"] > 64 * st["frames"] // 2  # the buffer did overflow
+
+
+def test_front_list_overflow_falls_back_to_the_block():
+    """More tokens close to the best than the front list holds (2048)."""
+    g = synth.make_random_fst(num_states=9000, num_arcs=120000, vocab=25, eps_frac=0.05, seed=77)
+    rng = np.random.default_rng(5)
+    T = 8
+    mats = []
+    for u in range(2):
+        x = rng.standard_normal((T, 25)).astype(np.float32) * np.float32(0.05)
+        x -= np.log(np.exp(x).sum(axis=1, keepdims=True))
+        mats.append(x.astype(np.float32))
+    o = dict(beam=40.0, max_active=2**31 - 1, min_active=0)
+    _, peak_tokens = _every_frame(g, o, mats, hash_capacity=1 << 16, arena_records=1 << 19)
+    assert peak_tokens > 4096
+
+
 def test_wide_rows_take_the_global_memory_path():
     """More columns than fit the shared-memory row staging: the row is gathered from global
     memory (no label order); results must not change."""
