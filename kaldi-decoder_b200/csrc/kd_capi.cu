@@ -211,6 +211,8 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
   switch (threads) {
     case 128:
       return LaunchAdvanceT<128, 7>(d, P, n_items, s);
+    case 160:
+      return LaunchAdvanceT<160, 7>(d, P, n_items, s);
     case 192:
       return LaunchAdvanceT<192, 5>(d, P, n_items, s);
     case 256:
@@ -218,7 +220,7 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
     case 512:
       return LaunchAdvanceT<512, 1>(d, P, n_items, s);
     default:
-      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 192, 256 or 512");
+      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 160, 192, 256 or 512");
   }
 }
 
@@ -493,10 +495,10 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->lcap = p2 / 2;
   d->qcap = p2;
   d->ccap = p2 / 4;
-  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 192 &&
+  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 && c.threads_per_lane != 192 &&
       c.threads_per_lane != 256 && c.threads_per_lane != 512) {
     delete d;
-    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 192, 256 or 512");
+    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 256 or 512");
   }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
   d->chunk_frames = c.chunk_frames > 0 ? c.chunk_frames : 128;

@@ -185,21 +185,12 @@ __device__ __forceinline__ float funkey(uint32_t k) {
   return __uint_as_float(u);
 }
 
-// Exact float -> double widening on the integer pipe.  The hardware conversion
-// (F2F.F64.F32) runs on the XU pipe, which two conversions per visited arc
-// saturate (ncu: sm__inst_executed_pipe_xu at its peak with 7 lanes per SM,
-// profiles/r1_v5_ncu_summary.txt); zero and normal numbers are rebuilt from
-// their bits instead, and only denormals, inf and NaN take the XU path.
-__device__ __forceinline__ double widen(float f) {
-  const uint32_t u = __float_as_uint(f);
-  const uint32_t mag = u & 0x7FFFFFFFu;
-  if (mag - 0x00800000u < 0x7F000000u) {  // normal: 0x00800000 <= mag < 0x7F800000
-    const uint32_t hi = (u & 0x80000000u) | ((mag >> 3) + (896u << 20));
-    return __hiloint2double(static_cast<int>(hi), static_cast<int>(u << 29));
-  }
-  if (mag == 0) return __hiloint2double(static_cast<int>(u), 0);  // +-0
-  return static_cast<double>(f);
-}
+// float -> double (exact).  The hardware conversion (F2F.F64.F32, XU pipe) is one
+// instruction; when every visited arc was evaluated it saturated the XU pipe and an
+// integer-pipe bit rebuild was faster (profiles/r1_v5_ncu_summary.txt).  With label
+// lookups a tenth of the arcs is evaluated and the single instruction wins again
+// (measured 108.8 -> 103.5 ms per launch).
+__device__ __forceinline__ double widen(float f) { return static_cast<double>(f); }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -270,7 +261,10 @@ struct Shared {
 
 // min over the block of (v, idx); ties -> lowest idx.  All threads get it.
 template <int THREADS>
-__device__ __forceinline__ void block_min_arg(double v, int idx, Shared &sh, double *out_v,
+#ifndef KD_INLINE_MIN
+#define KD_INLINE_MIN __noinline__
+#endif
+__device__ KD_INLINE_MIN void block_min_arg(double v, int idx, Shared &sh, double *out_v,
                                               int *out_i) {
   constexpr int NW = THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -423,7 +417,7 @@ __device__ uint32_t block_count_le(const double *cost, int n, double bound, Shar
 
 // GetCutoff's order statistic: the k-th smallest (0-based) of float(cost[i]).
 template <int THREADS>
-__device__ float select_kth(const double *cost, int n, uint32_t k, Shared &sh) {
+__device__ __noinline__ float select_kth(const double *cost, int n, uint32_t k, Shared &sh) {
   uint32_t prefix = 0, mask = 0;
   for (int pass = 3; pass >= 0; --pass) {
     const int shift = pass * 8;
@@ -735,16 +729,15 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
 // The key and the value of the first probed slot are loaded together (same
 // 32-byte sector): the usual case -- the state already has its slot -- then costs
 // one round trip before the 128-bit CAS instead of two.
-__device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
-                                           uint32_t a, unsigned long long nk, uint32_t tok_abs) {
-  const int2 no = __ldg(P.e_no + a);
+__device__ __forceinline__ void insert_probed(const Params &P, const LaneBuf &B, Shared &sh,
+                                              uint32_t a, unsigned long long nk, uint32_t tok_abs,
+                                              int2 no, int32_t k0, HVal cur) {
+  // `no` = e_no[a]; (k0, cur) = (key, value) read from the first probed slot of its state
   const int32_t state = no.x & 0x7FFFFFFF;
   HVal mine;
   mine.cost = nk;
   mine.arg = (static_cast<unsigned long long>(a) << 32) | tok_abs;
   const uint32_t h0 = table_hash(P, state);
-  const int32_t k0 = __ldcg(&B.table[h0].key);
-  HVal cur = ld_hval(&B.table[h0].val);  // same sector as the key: one round trip for both
   uint32_t h = h0;
   if (k0 != state) {
     h = table_slot_from(P, B, sh, state, h0, k0, no.x < 0 ? B.queue : nullptr, &sh.q_n[0]);
@@ -758,6 +751,20 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
     cur = got;
   }
 }
+
+__device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
+                                           uint32_t a, unsigned long long nk, uint32_t tok_abs) {
+  const int2 no = __ldg(P.e_no + a);
+  const uint32_t h0 = table_hash(P, no.x & 0x7FFFFFFF);
+  const int32_t k0 = __ldcg(&B.table[h0].key);
+  const HVal cur = ld_hval(&B.table[h0].val);  // same sector as the key: one round trip for both
+  insert_probed(P, B, sh, a, nk, tok_abs, no, k0, cur);
+}
+
+#ifndef KD_RECOMBINE
+#define KD_RECOMBINE 1
+#endif
+constexpr int kRecombine = KD_RECOMBINE;  // candidates a thread recombines together
 
 constexpr int kWindows = 4;  // 32-arc windows a warp keeps in flight
 
@@ -1178,10 +1185,47 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // ---------------------------------------------------------------- recombine
   const uint32_t n_cand = min(sh.cand_n, P.ccap);
   if (tid == 0) ls.st_cand += sh.cand_n;
-  for (uint32_t e = tid; e < n_cand; e += THREADS) {
-    const uint4 c = __ldcs(B.cand + e);
-    const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
-    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);  // faster-decoder.cc:211, final cutoff
+  // kRecombine candidates per thread are taken through the dependent loads together
+  // (candidate -> arc's (nextstate, olabel) -> first probe of the table); only the
+  // claim / CAS tail runs one candidate at a time.  A first probe that went stale
+  // meanwhile is caught by the claim and CAS loops.
+  for (uint32_t e0 = 0; e0 < n_cand; e0 += THREADS * kRecombine) {
+    uint4 c[kRecombine];
+    int2 no[kRecombine];
+    int32_t k0[kRecombine];
+    HVal cur[kRecombine];
+    bool ok[kRecombine];
+#pragma unroll
+    for (int u = 0; u < kRecombine; ++u) {
+      const uint32_t e = e0 + u * THREADS + tid;
+      ok[u] = e < n_cand;
+      c[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
+      if (ok[u]) c[u] = __ldcs(B.cand + e);
+      // faster-decoder.cc:211, final cutoff
+      ok[u] = ((static_cast<unsigned long long>(c[u].y) << 32) | c[u].x) < cstar_key;
+    }
+#pragma unroll
+    for (int u = 0; u < kRecombine; ++u) {
+      no[u] = make_int2(0, 0);
+      if (ok[u]) no[u] = __ldg(P.e_no + c[u].z);
+    }
+#pragma unroll
+    for (int u = 0; u < kRecombine; ++u) {
+      k0[u] = kEmptyKey;
+      cur[u].cost = kEmptyCost;
+      cur[u].arg = kEmptyArg;
+      if (ok[u]) {
+        const uint32_t h0 = table_hash(P, no[u].x & 0x7FFFFFFF);
+        k0[u] = __ldcg(&B.table[h0].key);
+        cur[u] = ld_hval(&B.table[h0].val);  // same sector as the key
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRecombine; ++u) {
+      if (!ok[u]) continue;
+      const unsigned long long nk = (static_cast<unsigned long long>(c[u].y) << 32) | c[u].x;
+      insert_probed(P, B, sh, c[u].z, nk, c[u].w, no[u], k0[u], cur[u]);
+    }
   }
   __syncthreads();
   if (tid == 0) {
