@@ -175,7 +175,7 @@ kd::Params MakeParams(const kd_decoder *d) {
 
 int PickThreads(const kd_decoder *d, int n_items) {
   if (d->threads > 0) return d->threads;
-  if (n_items >= 4 * d->num_sms) return 128;
+  if (n_items >= 4 * d->num_sms) return 160;
   if (n_items >= 2 * d->num_sms) return 256;
   return 512;
 }

@@ -92,10 +92,12 @@ struct __align__(16) LaneState {
   int32_t best_idx;        // index (in the current token block) of a best token
   int32_t n_live;          // tokens alive (the reference's toks_ list length)
   int32_t n_front;         // tokens below good_cut; the first kFrontCap of them are in the front list
+  int32_t n_mid;           // tokens below mid_cut
   uint32_t tok_base;       // arena index of the current token block
   uint32_t arena_used;     // arena records in use
   double best_cost;        // min cost over the current tokens (+inf if none)
   double good_cut;         // tokens below it are scanned first in the next frame
+  double mid_cut;          // n_mid tokens lie below it (lets GetCutoff skip its counting pass)
   // counters (kd_stats)
   long long st_frames, st_tokens_in, st_expanded, st_emit_arcs, st_eps_arcs,
       st_tokens_out, st_max_tokens, st_sweeps;
@@ -247,6 +249,7 @@ struct Shared {
   double wc;        // this frame's weight_cutoff
   uint32_t n_dead;  // commit: slot-list entries that are not tokens
   uint32_t n_front; // commit: tokens below good_cut
+  uint32_t n_mid;   // commit: tokens below mid_cut
   uint32_t count;
   uint32_t sel_bin, sel_k;
   // the frame's labels ordered by bucket of their acoustic cost (-log-prob - minimum):
@@ -405,6 +408,7 @@ __device__ uint32_t block_count_le(const double *cost, int n, double bound, Shar
   if (threadIdx.x == 0) sh.count = 0;
   __syncthreads();
   uint32_t c = 0;
+#pragma unroll 1
   for (int i = threadIdx.x; i < n; i += THREADS)
     c += (static_cast<double>(static_cast<float>(cost[i])) <= bound) ? 1u : 0u;
   c = __reduce_add_sync(0xFFFFFFFFu, c);
@@ -423,6 +427,7 @@ __device__ __noinline__ float select_kth(const double *cost, int n, uint32_t k, 
     const int shift = pass * 8;
     for (int i = threadIdx.x; i < 256; i += THREADS) sh.hist[i] = 0;
     __syncthreads();
+#pragma unroll 1
     for (int i = threadIdx.x; i < n; i += THREADS) {
       uint32_t u = fkey(static_cast<float>(cost[i]));
       if ((u & mask) == prefix) atomicAdd(&sh.hist[(u >> shift) & 255u], 1u);
@@ -462,8 +467,10 @@ __device__ __noinline__ float select_kth(const double *cost, int n, uint32_t k, 
 // sort behind every token), best = min cost.  All threads return
 // the same (weight_cutoff, adaptive_beam).
 template <int THREADS>
-__device__ void lane_cutoff(const Params &P, const double *cost, int n, int n_live, double best,
+__device__ void lane_cutoff(const Params &P, const double *cost, int n, const LaneState &ls,
                             Shared &sh, double *weight_cutoff, float *adaptive_beam) {
+  const int n_live = ls.n_live;
+  const double best = ls.best_cost;
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   if (P.max_active == 0x7FFFFFFF && P.min_active == 0) {
     *adaptive_beam = P.beam;
@@ -486,7 +493,14 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, int n_li
       // The (min_active+1)-th smallest exceeds beam_cutoff iff at most
       // min_active values are <= beam_cutoff: one counting pass decides
       // whether the exact order statistic is needed at all.
-      const uint32_t c = block_count_le<THREADS>(cost, n, beam_cutoff, sh);
+      // The commit already counted the tokens below mid_cut: when that bound lies safely
+      // (float rounding of the costs) below beam_cutoff they all count, and no pass is needed.
+      uint32_t c;
+      if (ls.n_mid > P.min_active && ls.mid_cut <= beam_cutoff - 1e-5 * (fabs(beam_cutoff) + 1.0)) {
+        c = static_cast<uint32_t>(ls.n_mid);
+      } else {
+        c = block_count_le<THREADS>(cost, n, beam_cutoff, sh);
+      }
       if (c > static_cast<uint32_t>(P.min_active)) {
         min_cut = beam_cutoff;  // some value <= beam_cutoff: min_active does not bind
       } else {
@@ -574,17 +588,20 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
 // rejects become candidates.
 template <int THREADS>
 __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
-                                        LaneState &ls, double cstar, double good_cut) {
+                                        LaneState &ls, double cstar, double good_cut,
+                                        double mid_cut) {
   const int tid = threadIdx.x;
   const unsigned long long cstar_key = dkey(cstar);
   // good_cut <= C*: every entry below it is a token
   const unsigned long long good_key = dkey(fmin(good_cut, cstar));
+  const unsigned long long mid_key = dkey(fmin(mid_cut, cstar));
   const double inf = __longlong_as_double(0x7FF0000000000000ll);
   const long long t_begin = clock64();
   if (tid == 0) {
     sh.q_n[1] = 0;
     sh.n_dead = 0;
     sh.n_front = 0;
+    sh.n_mid = 0;
     sh.acc_eps = 0;
   }
   __syncthreads();
@@ -621,7 +638,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   const bool write_ok = (sh.status & kStatusArenaOverflow) == 0;
   double my_min = inf;
   int my_arg = -1;
-  uint32_t dead = 0;
+  uint32_t dead = 0, below_mid = 0;
   for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {
     uint32_t h[4];
     HVal v[4];
@@ -668,6 +685,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       const bool live =
           v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
       if (!live) ++dead;
+      if (v[u].cost < mid_key) ++below_mid;
       if (write_ok) {
         const uint32_t arc = static_cast<uint32_t>(v[u].arg >> 32);
         uint32_t prev = static_cast<uint32_t>(v[u].arg);
@@ -697,6 +715,8 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   if ((tid & 31) == 0 && eps_count) atomicAdd(&sh.acc_eps, eps_count);
   dead = __reduce_add_sync(0xFFFFFFFFu, dead);
   if ((tid & 31) == 0 && dead) atomicAdd(&sh.n_dead, dead);
+  below_mid = __reduce_add_sync(0xFFFFFFFFu, below_mid);
+  if ((tid & 31) == 0 && below_mid) atomicAdd(&sh.n_mid, below_mid);
   __syncthreads();
   if (tid == 0) {
     if (write_ok) {
@@ -708,6 +728,8 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.best_idx = barg;
       ls.good_cut = fmin(good_cut, cstar);
       ls.n_front = static_cast<int32_t>(sh.n_front);
+      ls.mid_cut = fmin(mid_cut, cstar);
+      ls.n_mid = static_cast<int32_t>(sh.n_mid);
     } else {
       ls.n_tok = 0;
       ls.n_live = 0;
@@ -766,7 +788,10 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
 #endif
 constexpr int kRecombine = KD_RECOMBINE;  // candidates a thread recombines together
 
-constexpr int kWindows = 4;  // 32-arc windows a warp keeps in flight
+#ifndef KD_WINDOWS
+#define KD_WINDOWS 1
+#endif
+constexpr int kWindows = KD_WINDOWS;  // 32-arc windows a warp keeps in flight
 
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
 //
@@ -832,7 +857,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   }
   double wc;
   float abf;
-  lane_cutoff<THREADS>(P, cost, n, ls.n_live, ls.best_cost, sh, &wc, &abf);
+  lane_cutoff<THREADS>(P, cost, n, ls, sh, &wc, &abf);
   const double ab = static_cast<double>(abf);
   if (tid == 0) sh.wc = wc;
   __syncthreads();
@@ -1314,7 +1339,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
           P, B, sh, ls, row_g, s_row, t_cost, t_ex, t_beg, t_tab, t_tok, lab_order, bin_start);
       // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
       lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
-                                       cstar - 0.75 * static_cast<double>(P.beam));
+                                       cstar - 0.75 * static_cast<double>(P.beam),
+                                       cstar - 0.25 * static_cast<double>(P.beam));
       if (tid == 0) {
         ls.frames_decoded = frame + 1;
         ls.st_frames += 1;
@@ -1368,7 +1394,8 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
   }
   __syncthreads();
-  lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */, 0.0);
+  lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */, 0.0,
+                                   0.0);
   if (tid == 0) {
     ls.status = sh.status;
     ls.st_sweeps = 0;
