@@ -157,6 +157,15 @@ KD_API int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *l
                                       const int64_t *out_offsets, int64_t total_arcs,
                                       int32_t *ilabel, int32_t *olabel, float *graph_cost,
                                       float *acoustic_cost, float *final_weight2);
+/* Step 2 without the copy into caller arrays: the pointers returned address the
+ * decoder's own pinned host buffer (same layout: lane lanes[i]'s arcs at
+ * out_offsets[i]..) and stay valid until the next best-path call on this decoder
+ * or its destruction. */
+KD_API int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
+                                     const int64_t *out_offsets, int64_t total_arcs,
+                                     const int32_t **ilabel, const int32_t **olabel,
+                                     const float **graph_cost, const float **acoustic_cost,
+                                     float *final_weight2);
 /* Single-lane convenience: both steps; *num_arcs is the path length even if it
  * exceeds cap (then nothing is written and KD_ERR_INVALID is returned). */
 KD_API int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs, int64_t cap,

@@ -99,8 +99,8 @@ struct kd_decoder {
   // growable device scratch
   float *d_stage = nullptr;
   size_t stage_floats = 0;
-  int32_t *d_il = nullptr, *d_ol = nullptr;
-  float *d_gw = nullptr, *d_aw = nullptr;
+  int32_t *d_path = nullptr;  // best paths: [ilabel | olabel | graph | acoustic], path_cap words each
+  int32_t *h_path = nullptr;  // pinned mirror
   int64_t path_cap = 0;
 
   // pinned host mirrors
@@ -595,10 +595,8 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->d_counters);
   cudaFree(d->d_out_off);
   cudaFree(d->d_stage);
-  cudaFree(d->d_il);
-  cudaFree(d->d_ol);
-  cudaFree(d->d_gw);
-  cudaFree(d->d_aw);
+  cudaFree(d->d_path);
+  if (d->h_path) cudaFreeHost(d->h_path);
   if (d->h_items) cudaFreeHost(d->h_items);
   if (d->h_progress) cudaFreeHost(d->h_progress);
   if (d->h_lanes) cudaFreeHost(d->h_lanes);
@@ -891,12 +889,17 @@ int kd_decoder_best_path_prepare(kd_decoder *d, int32_t n, const int32_t *lanes,
   return KD_OK;
 }
 
-int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
-                               const int64_t *out_offsets, int64_t total_arcs, int32_t *ilabel,
-                               int32_t *olabel, float *graph_cost, float *acoustic_cost,
-                               float *final_weight2) {
+int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
+                              const int64_t *out_offsets, int64_t total_arcs,
+                              const int32_t **ilabel, const int32_t **olabel,
+                              const float **graph_cost, const float **acoustic_cost,
+                              float *final_weight2) {
   int rc = CheckLanes(d, n, lanes);
   if (rc) return rc;
+  if (ilabel) *ilabel = nullptr;
+  if (olabel) *olabel = nullptr;
+  if (graph_cost) *graph_cost = nullptr;
+  if (acoustic_cost) *acoustic_cost = nullptr;
   if (n == 0) return KD_OK;
   if (!out_offsets || total_arcs < 0) return Fail(KD_ERR_INVALID, "bad output layout");
   KD_CUDA(cudaSetDevice(d->device));
@@ -916,17 +919,13 @@ int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (total_arcs == 0) return KD_OK;
   if (total_arcs > d->path_cap) {
     KD_CUDA(cudaDeviceSynchronize());
-    cudaFree(d->d_il);
-    cudaFree(d->d_ol);
-    cudaFree(d->d_gw);
-    cudaFree(d->d_aw);
-    d->d_il = d->d_ol = nullptr;
-    d->d_gw = d->d_aw = nullptr;
+    cudaFree(d->d_path);
+    if (d->h_path) cudaFreeHost(d->h_path);
+    d->d_path = d->h_path = nullptr;
     d->path_cap = 0;
-    size_t cap = static_cast<size_t>(total_arcs) + static_cast<size_t>(total_arcs) / 4 + 1024;
-    if ((rc = DevAlloc(&d->d_il, cap)) || (rc = DevAlloc(&d->d_ol, cap)) ||
-        (rc = DevAlloc(&d->d_gw, cap)) || (rc = DevAlloc(&d->d_aw, cap)))
-      return rc;
+    const size_t cap = static_cast<size_t>(total_arcs) + static_cast<size_t>(total_arcs) / 4 + 1024;
+    if ((rc = DevAlloc(&d->d_path, 4 * cap))) return rc;
+    KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_path), 4 * cap * sizeof(int32_t)));
     d->path_cap = static_cast<int64_t>(cap);
   }
   cudaStream_t s = d->streams[0];
@@ -936,20 +935,37 @@ int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
                           cudaMemcpyHostToDevice, s));
   kd::Params P = MakeParams(d);
   P.n_items = n;
-  const int tb = 32;
-  kd::kd_best_fill_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(P, d->d_out_off, d->d_il, d->d_ol,
-                                                         d->d_gw, d->d_aw);
-  KD_CUDA(cudaGetLastError());
+  // the four arrays are packed total_arcs apart: one contiguous copy brings them back
   const size_t nb = static_cast<size_t>(total_arcs);
-  if (ilabel)
-    KD_CUDA(cudaMemcpyAsync(ilabel, d->d_il, nb * 4, cudaMemcpyDeviceToHost, s));
-  if (olabel)
-    KD_CUDA(cudaMemcpyAsync(olabel, d->d_ol, nb * 4, cudaMemcpyDeviceToHost, s));
-  if (graph_cost)
-    KD_CUDA(cudaMemcpyAsync(graph_cost, d->d_gw, nb * 4, cudaMemcpyDeviceToHost, s));
-  if (acoustic_cost)
-    KD_CUDA(cudaMemcpyAsync(acoustic_cost, d->d_aw, nb * 4, cudaMemcpyDeviceToHost, s));
+  int32_t *d_il = d->d_path, *d_ol = d->d_path + nb;
+  float *d_gw = reinterpret_cast<float *>(d->d_path + 2 * nb);
+  float *d_aw = reinterpret_cast<float *>(d->d_path + 3 * nb);
+  const int tb = 32;
+  kd::kd_best_fill_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(P, d->d_out_off, d_il, d_ol, d_gw, d_aw);
+  KD_CUDA(cudaGetLastError());
+  KD_CUDA(cudaMemcpyAsync(d->h_path, d->d_path, 4 * nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   KD_CUDA(cudaStreamSynchronize(s));
+  if (ilabel) *ilabel = d->h_path;
+  if (olabel) *olabel = d->h_path + nb;
+  if (graph_cost) *graph_cost = reinterpret_cast<const float *>(d->h_path + 2 * nb);
+  if (acoustic_cost) *acoustic_cost = reinterpret_cast<const float *>(d->h_path + 3 * nb);
+  return KD_OK;
+}
+
+int kd_decoder_best_path_fetch(kd_decoder *d, int32_t n, const int32_t *lanes,
+                               const int64_t *out_offsets, int64_t total_arcs, int32_t *ilabel,
+                               int32_t *olabel, float *graph_cost, float *acoustic_cost,
+                               float *final_weight2) {
+  const int32_t *il = nullptr, *ol = nullptr;
+  const float *gw = nullptr, *aw = nullptr;
+  int rc = kd_decoder_best_path_view(d, n, lanes, out_offsets, total_arcs, &il, &ol, &gw, &aw,
+                                     final_weight2);
+  if (rc || total_arcs <= 0 || il == nullptr) return rc;
+  const size_t bytes = static_cast<size_t>(total_arcs) * 4;
+  if (ilabel) memcpy(ilabel, il, bytes);
+  if (olabel) memcpy(olabel, ol, bytes);
+  if (graph_cost) memcpy(graph_cost, gw, bytes);
+  if (acoustic_cost) memcpy(acoustic_cost, aw, bytes);
   return KD_OK;
 }
 

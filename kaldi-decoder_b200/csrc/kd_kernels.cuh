@@ -847,8 +847,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29),
   // already negated (faster-decoder.cc:209); widened to fp64 where it is used.
   // (Shared memory is kept small on purpose: what it does not take is L1.)
+  float amin = __int_as_float(0x7F800000);  // smallest acoustic cost of the frame (ROW_SMEM)
   if (ROW_SMEM) {
-    for (int i = tid; i < P.cols; i += THREADS) s_row[i] = -__ldg(row_g + i);
+    for (int i = tid; i < P.cols; i += THREADS) {
+      const float v = -__ldg(row_g + i);
+      s_row[i] = v;
+      amin = fminf(amin, v);
+    }
   }
   if (tid == 0) {
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
@@ -868,13 +873,15 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     // the tile arrays (t_cost .. t_tok, contiguous, 6 * TT words) are free until the scan
     uint32_t *hist = reinterpret_cast<uint32_t *>(t_cost);
     static_assert(6 * TT >= kOrderBins, "tile arrays too small to hold the label histogram");
-    float amin = __int_as_float(0x7F800000);
-    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, s_row[i]);
+#pragma unroll 1
     for (int b = tid; b < kOrderBins; b += THREADS) hist[b] = 0;
     double dmin;
     int dummy;
     block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
     amin = static_cast<float>(dmin);
+    // (these loops touch shared memory only: not unrolled, the kernel is short of
+    // instruction cache, not of latency hiding here)
+#pragma unroll 1
     for (int i = tid; i < P.cols; i += THREADS) {
       const float d = (s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
@@ -915,6 +922,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       }
     }
     __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < P.cols; i += THREADS) {
       const float d = (s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
@@ -925,15 +933,31 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     if (tid == 0) sh.order_ok = 0;
     __syncthreads();
   }
-  // seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189)
+  // Seed the running cutoff from the best token's arcs (faster-decoder.cc:176-189).  Any
+  // subset of its arcs gives a valid (if looser) bound: a state with a label table
+  // only looks up the THREADS labels with the best acoustic cost.
   double seed = inf;
   if (n > 0 && ls.best_cost < wc) {
-    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(state[ls.best_idx]));
-    for (int a = tid; a < st.y; a += THREADS) {
-      const int2 iw = __ldg(P.e_iw + st.x + a);
-      const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
-      const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
-      seed = fmin(seed, nw);
+    const int32_t bs = state[ls.best_idx];
+    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(bs));
+    const int4 sb = __ldg(P.st + 2 * static_cast<size_t>(bs) + 1);
+    if (sh.order_ok != 0 && sb.x >= 0) {
+      if (tid < P.cols) {
+        const uint32_t lab = lab_order[tid];
+        const uint32_t off = __ldg(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
+        if (off != 0xFFFFu) {
+          const int2 iw = __ldg(P.e_iw + st.x + off);
+          seed = (widen(__int_as_float(iw.y)) + ls.best_cost) + widen(s_row[lab - 1]);
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int a = tid; a < st.y; a += THREADS) {
+        const int2 iw = __ldg(P.e_iw + st.x + a);
+        const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
+        const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
+        seed = fmin(seed, nw);
+      }
     }
   }
   {
@@ -958,14 +982,22 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // (Loop state is kept in shared memory where it can be: the item loop below needs
   // every register it can get.)
   static_assert(TT <= kFrontCap, "front list smaller than a scan tile");
+#ifdef KD_NO_FRONT
+  for (int pass = 1; pass < 2; ++pass) {
+#else
   for (int pass = 0; pass < 2; ++pass) {
+#endif
     // pass 0 reads the front list the commit wrote, unless it overflowed (then it filters the block)
     const bool front_list =
         pass == 0 && static_cast<uint32_t>(ls.n_front) <= static_cast<uint32_t>(kFrontCap);
     const uint32_t un = static_cast<uint32_t>(front_list ? ls.n_front : ls.n_tok);
     for (uint32_t tile0 = 0; tile0 < un; tile0 += TT) {
     const double wcut = sh.wc;
+#ifdef KD_NO_FRONT
+    const double good = -inf;
+#else
     const double good = fmin(ls.good_cut, wcut);
+#endif
     const uint32_t tile_end = min(un, tile0 + TT);
     // chunk setup: 4 consecutive tokens per thread -> (cost, arc range or label
     // count) of the tokens to expand
@@ -1498,11 +1530,14 @@ __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t 
   long long pos = out_off[b] + L->bp_len - 1;
   uint32_t t = L->bp_best_tok;
   double c = B.a_cost[t];
+  unsigned long long link = B.a_link[t];
   while (true) {
-    unsigned long long link = B.a_link[t];
     uint32_t arc = static_cast<uint32_t>(link >> 32);
     if (arc == kNoArc) break;
     uint32_t prev = static_cast<uint32_t>(link);
+    // the pointer chase is the critical path: its next load goes out before the
+    // loads that only feed this step's output
+    const unsigned long long link_next = B.a_link[prev];
     double pc = B.a_cost[prev];
     int32_t ilab, olab;
     float graph;
@@ -1526,6 +1561,7 @@ __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t 
     --pos;
     t = prev;
     c = pc;
+    link = link_next;
   }
 }
 

@@ -50,7 +50,8 @@ EXPORTED = (
     "kd_last_error", "kd_device_count", "kd_graph_create", "kd_graph_destroy", "kd_graph_info",
     "kd_decoder_create", "kd_decoder_destroy", "kd_decoder_set_options", "kd_decoder_init",
     "kd_decoder_advance", "kd_decoder_num_frames_decoded", "kd_decoder_reached_final",
-    "kd_decoder_best_path_prepare", "kd_decoder_best_path_fetch", "kd_decoder_best_path",
+    "kd_decoder_best_path_prepare", "kd_decoder_best_path_fetch", "kd_decoder_best_path_view",
+    "kd_decoder_best_path",
     "kd_decoder_dump_tokens", "kd_decoder_stats", "kd_decoder_last_advance_info",
     "kd_decoder_info",
 )
@@ -81,6 +82,8 @@ def lib():
         L.kd_decoder_reached_final.argtypes = [vp, i32, C.POINTER(i32)]
         L.kd_decoder_best_path_prepare.argtypes = [vp, i32, vp, C.c_int, vp, vp, vp]
         L.kd_decoder_best_path_fetch.argtypes = [vp, i32, vp, vp, i64, vp, vp, vp, vp, vp]
+        L.kd_decoder_best_path_view.argtypes = [vp, i32, vp, vp, i64, C.POINTER(vp), C.POINTER(vp),
+                                                C.POINTER(vp), C.POINTER(vp), vp]
         L.kd_decoder_best_path.argtypes = [vp, i32, C.c_int, i64, vp, vp, vp, vp,
                                            C.POINTER(i64), vp, C.POINTER(i32), C.POINTER(i32)]
         L.kd_decoder_dump_tokens.argtypes = [vp, i32, i64, vp, vp, C.POINTER(i64)]
@@ -174,6 +177,32 @@ class RawPath:
                      + float(self.final[0]) + float(self.final[1]))
 
 
+class PathBatch:
+    """The best paths of a batch of lanes: flat arc arrays + offsets; item i is a RawPath
+    (views into the flat arrays, no per-lane copies)."""
+
+    def __init__(self, ok, reached_final, offsets, il, ol, gw, aw, final):
+        self.ok, self.reached_final, self.offsets = ok, reached_final, offsets
+        self.ilabels, self.olabels, self.graph, self.acoustic, self.final = il, ol, gw, aw, final
+
+    def __len__(self):
+        return int(self.ok.shape[0])
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        return RawPath(self.ok[i], self.reached_final[i], self.ilabels[a:b], self.olabels[a:b],
+                       self.graph[a:b], self.acoustic[a:b], self.final[i])
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class LaneDecoder:
     """kd_decoder: `max_lanes` independent utterance lanes on one GPU."""
 
@@ -240,7 +269,10 @@ class LaneDecoder:
         _check(lib().kd_decoder_reached_final(self.h, int(lane), C.byref(v)))
         return bool(v.value)
 
-    def best_paths(self, lanes, use_final_probs: bool = True) -> List[RawPath]:
+    def best_paths(self, lanes, use_final_probs: bool = True, copy: bool = True) -> "PathBatch":
+        """Best path of every lane in `lanes` (a sequence of RawPath, built on demand).
+        copy=False leaves the arcs in the decoder's pinned host buffer: the result is
+        only valid until the next best_paths() call on this decoder."""
         la = self._lanes(lanes)
         n = la.size
         ok = np.zeros(n, np.int32)
@@ -248,23 +280,22 @@ class LaneDecoder:
         cnt = np.zeros(n, np.int64)
         _check(lib().kd_decoder_best_path_prepare(self.h, n, la.ctypes.data, int(use_final_probs),
                                                   ok.ctypes.data, rf.ctypes.data, cnt.ctypes.data))
-        off = np.zeros(n, np.int64)
-        off[1:] = np.cumsum(cnt)[:-1]
-        total = int(cnt.sum())
-        il = np.empty(total, np.int32)
-        ol = np.empty(total, np.int32)
-        gw = np.empty(total, np.float32)
-        aw = np.empty(total, np.float32)
+        off = np.zeros(n + 1, np.int64)
+        np.cumsum(cnt, out=off[1:])
+        total = int(off[n])
         f2 = np.zeros((n, 2), np.float32)
-        _check(lib().kd_decoder_best_path_fetch(self.h, n, la.ctypes.data, off.ctypes.data, total,
-                                                il.ctypes.data, ol.ctypes.data, gw.ctypes.data,
-                                                aw.ctypes.data, f2.ctypes.data))
-        out = []
-        for i in range(n):
-            a, b = int(off[i]), int(off[i] + cnt[i])
-            out.append(RawPath(ok[i], rf[i], il[a:b].copy(), ol[a:b].copy(), gw[a:b].copy(),
-                               aw[a:b].copy(), f2[i].copy()))
-        return out
+        ptr = [C.c_void_p() for _ in range(4)]
+        _check(lib().kd_decoder_best_path_view(self.h, n, la.ctypes.data, off.ctypes.data, total,
+                                               C.byref(ptr[0]), C.byref(ptr[1]), C.byref(ptr[2]),
+                                               C.byref(ptr[3]), f2.ctypes.data))
+        arrs = []
+        for p, dt in zip(ptr, (np.int32, np.int32, np.float32, np.float32)):
+            if total == 0 or not p.value:
+                arrs.append(np.empty(0, dt))
+                continue
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(total,)).view(dt)
+            arrs.append(a.copy() if copy else a)
+        return PathBatch(ok, rf, off, arrs[0], arrs[1], arrs[2], arrs[3], f2)
 
     def tokens(self, lane: int) -> Tuple[np.ndarray, np.ndarray]:
         n = C.c_int64(0)
