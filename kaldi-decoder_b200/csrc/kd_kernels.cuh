@@ -334,6 +334,29 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   return b;
 }
 
+// A slot that was just claimed joins this frame's slot list (its position there is the
+// token's number in the next block) and, when `eps_queue` is given (the state has
+// epsilon arcs), that queue: the closure only visits those.
+__device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B, Shared &sh,
+                                               uint32_t h, uint32_t *eps_queue,
+                                               uint32_t *eps_queue_n) {
+  const uint32_t pos = atomicAdd(&sh.list_n, 1u);
+  if (pos < P.lcap) {
+    B.list[pos] = h;
+    B.table[h].idx = pos;  // tokens are numbered in claim order
+  } else {
+    atomicOr(&sh.status, kStatusHashOverflow);
+  }
+  if (eps_queue != nullptr) {
+    const uint32_t qp = atomicAdd(eps_queue_n, 1u);
+    if (qp < P.qcap) {
+      eps_queue[qp] = h;
+    } else {
+      atomicOr(&sh.status, kStatusQueueOverflow);
+    }
+  }
+}
+
 // Finds the table slot of `state`, claiming an empty one if needed.  Probes are
 // plain loads; an atomic is spent only on an empty slot.  (Probing with the
 // CAS itself saves a round trip for new states but turns every arrival at an
@@ -352,21 +375,7 @@ __device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneB
       k = atomicCAS(&B.table[h].key, kEmptyKey, state);
       if (k == state) return h;
       if (k == kEmptyKey) {
-        const uint32_t pos = atomicAdd(&sh.list_n, 1u);
-        if (pos < P.lcap) {
-          B.list[pos] = h;
-          B.table[h].idx = pos;  // tokens are numbered in claim order
-        } else {
-          atomicOr(&sh.status, kStatusHashOverflow);
-        }
-        if (eps_queue != nullptr) {
-          const uint32_t qp = atomicAdd(eps_queue_n, 1u);
-          if (qp < P.qcap) {
-            eps_queue[qp] = h;
-          } else {
-            atomicOr(&sh.status, kStatusQueueOverflow);
-          }
-        }
+        register_claim(P, B, sh, h, eps_queue, eps_queue_n);
         return h;
       }
     }
@@ -783,10 +792,6 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
   insert_probed(P, B, sh, a, nk, tok_abs, no, k0, cur);
 }
 
-#ifndef KD_RECOMBINE
-#define KD_RECOMBINE 1
-#endif
-constexpr int kRecombine = KD_RECOMBINE;  // candidates a thread recombines together
 
 #ifndef KD_WINDOWS
 #define KD_WINDOWS 1
@@ -1242,47 +1247,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // ---------------------------------------------------------------- recombine
   const uint32_t n_cand = min(sh.cand_n, P.ccap);
   if (tid == 0) ls.st_cand += sh.cand_n;
-  // kRecombine candidates per thread are taken through the dependent loads together
-  // (candidate -> arc's (nextstate, olabel) -> first probe of the table); only the
-  // claim / CAS tail runs one candidate at a time.  A first probe that went stale
-  // meanwhile is caught by the claim and CAS loops.
-  for (uint32_t e0 = 0; e0 < n_cand; e0 += THREADS * kRecombine) {
-    uint4 c[kRecombine];
-    int2 no[kRecombine];
-    int32_t k0[kRecombine];
-    HVal cur[kRecombine];
-    bool ok[kRecombine];
-#pragma unroll
-    for (int u = 0; u < kRecombine; ++u) {
-      const uint32_t e = e0 + u * THREADS + tid;
-      ok[u] = e < n_cand;
-      c[u] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0, 0);
-      if (ok[u]) c[u] = __ldcs(B.cand + e);
-      // faster-decoder.cc:211, final cutoff
-      ok[u] = ((static_cast<unsigned long long>(c[u].y) << 32) | c[u].x) < cstar_key;
-    }
-#pragma unroll
-    for (int u = 0; u < kRecombine; ++u) {
-      no[u] = make_int2(0, 0);
-      if (ok[u]) no[u] = __ldg(P.e_no + c[u].z);
-    }
-#pragma unroll
-    for (int u = 0; u < kRecombine; ++u) {
-      k0[u] = kEmptyKey;
-      cur[u].cost = kEmptyCost;
-      cur[u].arg = kEmptyArg;
-      if (ok[u]) {
-        const uint32_t h0 = table_hash(P, no[u].x & 0x7FFFFFFF);
-        k0[u] = __ldcg(&B.table[h0].key);
-        cur[u] = ld_hval(&B.table[h0].val);  // same sector as the key
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kRecombine; ++u) {
-      if (!ok[u]) continue;
-      const unsigned long long nk = (static_cast<unsigned long long>(c[u].y) << 32) | c[u].x;
-      insert_probed(P, B, sh, c[u].z, nk, c[u].w, no[u], k0[u], cur[u]);
-    }
+  // (Measured and rejected: taking 2-4 candidates per thread through the dependent
+  // loads together -- the recombination gets faster, the other phases of the co-resident
+  // lanes slower by as much; claiming the slot with the CAS before any probe load.)
+  for (uint32_t e = tid; e < n_cand; e += THREADS) {
+    const uint4 c = __ldcs(B.cand + e);
+    const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
+    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);  // faster-decoder.cc:211, final cutoff
   }
   __syncthreads();
   if (tid == 0) {
