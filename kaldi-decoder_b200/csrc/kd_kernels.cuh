@@ -27,16 +27,14 @@
 // a state are resolved towards the lowest emitting-arc index (deterministic);
 // in the epsilon closure the incumbent stays (as in the reference).
 //
-// The search is latency bound, not bandwidth bound (profiles/r1_*): a lane-frame
-// is a chain of dependent L2 round trips executed by a handful of warps.  The
-// structure below is chosen to shorten that chain: the emitting arcs of a
-// whole tile of tokens are flattened (block prefix sum of out-degrees) so that
-// every thread keeps U independent 8-byte arc loads in flight; admitted arcs
-// (~3% of the visited ones) are parked in shared memory and recombined a
-// queue-full at a time; table operations start with a speculative CAS instead
-// of a load; the closure only visits states that have epsilon arcs (flag
-// carried in the arc record); the commit passes load four entries per thread
-// before using any.
+// What bounds the search (profiles/r1_*): not bandwidth but (a) the
+// dependent L2 round trips of a lane-frame, executed by 5 warps, (b) the work of the
+// 6 other lanes on the SM -- a lane alone runs 2.7x faster -- and (c) the instruction
+// cache: 7 lanes per SM are in 7 different phases of this kernel, and its body must stay
+// small (~3.5 k instructions; at 7 k a quarter of the issue cycles waited for fetches).
+// Hence: little unrolling, cold paths out of line, label tables so that a tenth of the
+// arcs is evaluated, candidates filtered by the exact cutoff before they touch the
+// table, a single-pass commit, and 32-byte table entries (one sector per state).
 #ifndef KD_KERNELS_CUH_
 #define KD_KERNELS_CUH_
 
