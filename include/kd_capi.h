@@ -65,10 +65,20 @@ typedef struct kd_decoder_config {
                                tokens alive in one frame must stay <= capacity / 2     */
   int64_t arena_records;    /* per-lane backpointer-store records (sum over frames of
                                tokens alive at frame end), 20 bytes each               */
-  int32_t threads_per_lane; /* 128/256/512/1024; default chosen from max_lanes         */
+  int32_t threads_per_lane; /* 128/160/192/256/512; default chosen per launch         */
   int32_t chunk_frames;     /* host-memory advance: frames per copy/search pipeline
                                stage (default 128)                                     */
+  int32_t search;           /* KD_SEARCH_FASTER (default) or KD_SEARCH_SIMPLE          */
 } kd_decoder_config;
+
+/* Which reference decoder the lanes reproduce.
+ *   KD_SEARCH_FASTER  FasterDecoder (faster-decoder.cc), all kd_options fields used.
+ *   KD_SEARCH_SIMPLE  SimpleDecoder (simple-decoder.cc:150-279): beam-only pruning
+ *                     (kd_options.beam; max_active / min_active are ignored), token cost
+ *                     = prev + float(w + ac), PruneToks applied to what ReachedFinal and
+ *                     GetBestPath see. */
+#define KD_SEARCH_FASTER 0
+#define KD_SEARCH_SIMPLE 1
 
 /* Search counters, summed over the frames decoded since kd_decoder_init.  They
  * define the algorithmic bytes of SURVEY.md §8(d):
@@ -143,6 +153,11 @@ KD_API int kd_decoder_num_frames_decoded(kd_decoder *d, int32_t lane, int32_t *o
 
 /* FasterDecoder::ReachedFinal (faster-decoder.cc:347-354). */
 KD_API int kd_decoder_reached_final(kd_decoder *d, int32_t lane, int32_t *out);
+
+/* SimpleDecoder::FinalRelativeCost (simple-decoder.cc:78-101): best cost with final
+ * weights minus best cost over the live tokens; +inf if no final state is active or
+ * no token is alive.  Either search mode. */
+KD_API int kd_decoder_final_relative_cost(kd_decoder *d, int32_t lane, float *out);
 
 /* FasterDecoder::GetBestPath (faster-decoder.cc:356-424) up to, and not
  * including, RemoveEpsLocal: one (ilabel, olabel, graph cost, acoustic cost)

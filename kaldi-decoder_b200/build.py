@@ -53,7 +53,8 @@ def build_pybind(force: bool = False) -> str:
     os.makedirs(PY_LIB_DIR, exist_ok=True)
     suffix = sysconfig.get_config_var("EXT_SUFFIX")
     out = os.path.join(PY_LIB_DIR, "_kaldi_decoder" + suffix)
-    names = ["faster-decoder.cc", "decodable-ctc.cc", "fst-io.cc", os.path.join("python", "module.cc")]
+    names = ["faster-decoder.cc", "simple-decoder.cc", "decodable-ctc.cc", "fst-io.cc",
+             os.path.join("python", "module.cc")]
     srcs = [os.path.join(CSRC, n) for n in names]
     hdrs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith(".h")]
     if not all(os.path.exists(s) for s in srcs):

@@ -34,6 +34,7 @@ kd_options ToC(const FasterDecoderOptions &o) {
 
 kd_decoder_config ToC(const DeviceConfig &d, int32_t max_lanes) {
   kd_decoder_config c;
+  c.search = KD_SEARCH_FASTER;
   c.max_lanes = max_lanes;
   c.hash_capacity = d.hash_capacity;
   c.arena_records = d.arena_records;

@@ -75,6 +75,7 @@ struct kd_decoder {
   uint32_t hcap = 0, lcap = 0, qcap = 0, ccap = 0;
   int64_t arena_cap = 0;
   int32_t threads = 0;  // 0 = auto per launch
+  int32_t simple = 0;   // KD_SEARCH_SIMPLE
   int32_t chunk_frames = 128;
   size_t device_bytes = 0;
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
@@ -142,14 +143,16 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.st = d->g->st;
   P.labtab = d->g->labtab;
   P.lab_stride = d->g->max_ilabel;
+  P.simple = d->simple;
   P.e_iw = d->g->e_iw;
   P.e_no = d->g->e_no;
   P.n_arc = d->g->n_arc;
   P.fin = d->g->fin;
   P.start = d->g->start;
   P.beam = d->opts.beam;
-  P.max_active = d->opts.max_active;
-  P.min_active = d->opts.min_active;
+  // SimpleDecoder has no max_active / min_active: GetCutoff degenerates to best + beam
+  P.max_active = d->simple ? 0x7FFFFFFF : d->opts.max_active;
+  P.min_active = d->simple ? 0 : d->opts.min_active;
   P.beam_delta = d->opts.beam_delta;
   P.lanes = d->lanes;
   P.items = d->d_items;
@@ -206,8 +209,33 @@ int LaunchAdvanceT(kd_decoder *d, const kd::Params &P, int n_items, cudaStream_t
                        : LaunchAdvanceR<THREADS, MIN_BLOCKS, false>(d, P, n_items, s);
 }
 
+// SimpleDecoder search: one instantiation (256 threads per lane), the mode is an API
+// completeness feature, not a tuned path.
+int LaunchAdvanceSimple(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
+  constexpr int THREADS = 256;
+  size_t smem = kd::advance_smem_fixed<THREADS>() + 16;
+  if (P.row_in_smem) smem += static_cast<size_t>(P.cols) * (sizeof(float) + sizeof(uint16_t));
+  auto launch = [&](auto kernel) -> int {
+    if (smem > 32 * 1024)
+      KD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+    int per_sm = 1;
+    KD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int grid = std::min(n_items, per_sm * d->num_sms);
+    kernel<<<grid, THREADS, smem, s>>>(P);
+    KD_CUDA(cudaGetLastError());
+    d->last_launches++;
+    d->last_blocks_per_sm = per_sm;
+    return KD_OK;
+  };
+  return P.row_in_smem ? launch(kd::kd_advance_kernel<THREADS, 3, true, true>)
+                       : launch(kd::kd_advance_kernel<THREADS, 3, false, true>);
+}
+
 int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
                   cudaStream_t s) {
+  if (d->simple) return LaunchAdvanceSimple(d, P, n_items, s);
   switch (threads) {
     case 128:
       return LaunchAdvanceT<128, 7>(d, P, n_items, s);
@@ -232,6 +260,8 @@ const char *StatusText(int st) {
   if (st & kd::kStatusQueueOverflow)
     return "epsilon worklist overflow (raise kd_decoder_config.hash_capacity)";
   if (st & kd::kStatusInputStall) return "streamed log-probs did not arrive (copy stalled)";
+  if (st & kd::kStatusCandOverflow)
+    return "candidate buffer overflow (raise kd_decoder_config.hash_capacity)";
   return "unknown device status";
 }
 
@@ -501,6 +531,11 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
     return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 256 or 512");
   }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
+  if (c.search != KD_SEARCH_FASTER && c.search != KD_SEARCH_SIMPLE) {
+    delete d;
+    return Fail(KD_ERR_INVALID, "kd_decoder_config.search must be KD_SEARCH_FASTER or KD_SEARCH_SIMPLE");
+  }
+  d->simple = c.search == KD_SEARCH_SIMPLE ? 1 : 0;
   d->chunk_frames = c.chunk_frames > 0 ? c.chunk_frames : 128;
 
   const size_t L = static_cast<size_t>(d->max_lanes);
@@ -986,6 +1021,20 @@ int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs, int64
   int64_t off = 0;
   return kd_decoder_best_path_fetch(d, 1, &lane, &off, len, ilabel, olabel, graph_cost,
                                     acoustic_cost, final_weight2);
+}
+
+int kd_decoder_final_relative_cost(kd_decoder *d, int32_t lane, float *out) {
+  int32_t okv = 0, rf = 0;
+  int64_t len = 0;
+  int rc = kd_decoder_best_path_prepare(d, 1, &lane, 1, &okv, &rf, &len);
+  if (rc) return rc;
+  const kd::LaneState &L = d->h_lanes[lane];
+  float v = std::numeric_limits<float>::infinity();
+  // with a final state active the selection cost is min(cost + final weight)
+  if (okv && rf) v = static_cast<float>(L.bp_value - L.best_cost);
+  if (v != v) v = std::numeric_limits<float>::infinity();  // simple-decoder.cc:94-98
+  if (out) *out = v;
+  return KD_OK;
 }
 
 int kd_decoder_reached_final(kd_decoder *d, int32_t lane, int32_t *out) {

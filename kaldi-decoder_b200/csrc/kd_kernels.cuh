@@ -47,6 +47,7 @@ constexpr int kStatusHashOverflow = 1;
 constexpr int kStatusArenaOverflow = 2;
 constexpr int kStatusQueueOverflow = 4;
 constexpr int kStatusInputStall = 8;  // streamed log-probs never arrived
+constexpr int kStatusCandOverflow = 16;  // SimpleDecoder search: candidate buffer full
 
 // In an arc field: "epsilon arc".  In a nextstate field: "state has epsilon arcs".
 constexpr uint32_t kEpsFlag = 0x80000000u;
@@ -109,6 +110,7 @@ struct __align__(16) LaneState {
   uint32_t bp_best_tok;    // arena index
   long long bp_len;
   float bp_final_w;
+  double bp_value;         // selection cost of the best token (cost, or cost + final weight)
 };
 
 struct AdvanceItem {
@@ -127,6 +129,7 @@ struct Params {
                        //      {label-table row or -1, smallest emitting weight bits, 0, 0}
   const uint16_t *labtab;  // [rows][lab_stride]: ilabel-1 -> arc offset within the state, 0xFFFF none
   int32_t lab_stride;
+  int32_t simple;      // 1: SimpleDecoder semantics (simple-decoder.cc), else FasterDecoder
   const int2 *e_iw;    // [Ee] {ilabel, weight bits}
   const int2 *e_no;    // [Ee] {nextstate | kEpsFlag if that state has eps arcs, olabel}
   const int4 *n_arc;   // [En] {olabel, weight bits, nextstate | kEpsFlag ..., 0}
@@ -530,6 +533,7 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, const La
 // phase with cost >= C* is not a token (see file comment) and is overwritten.
 // A token that was created or improved is queued for expansion when its state
 // has epsilon arcs (flag in the arc's nextstate word).
+template <bool SIMPLE>
 __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
                                             uint32_t dst_word, unsigned long long cost_key,
                                             uint32_t arc, uint32_t src_number,
@@ -544,7 +548,9 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
   HVal cur = ld_hval(&B.table[h].val);
   while (true) {
     const bool cur_is_eps = (cur.arg >> 63) != 0;
-    const bool replace = mine.cost < cur.cost || (!cur_is_eps && !(cur.cost < cstar_key));
+    // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
+    const bool replace =
+        mine.cost < cur.cost || (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
     if (!replace) return;
     HVal got = cas_hval(&B.table[h].val, cur, mine);
     if (got.cost == cur.cost && got.arg == cur.arg) break;
@@ -562,6 +568,7 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
 
 // Expands the epsilon arcs of the token in table slot `slot`
 // (faster-decoder.cc:71-117).
+template <bool SIMPLE>
 __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Shared &sh,
                                            uint32_t slot, unsigned long long cstar_key,
                                            double cstar, uint32_t *q_next, uint32_t *q_next_n,
@@ -569,7 +576,7 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   const HVal v = ld_hval(&B.table[slot].val);
   const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
-  if (v.cost == kEmptyCost || !(v.cost < cstar_key || is_eps)) return;
+  if (v.cost == kEmptyCost || !(SIMPLE || v.cost < cstar_key || is_eps)) return;
   const int2 ki = __ldcg(reinterpret_cast<const int2 *>(&B.table[slot].key));  // {state, number}
   const int4 st = __ldg(P.st + 2 * static_cast<size_t>(ki.x));
   if (st.w == 0) return;
@@ -579,7 +586,7 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
     const int4 arc = __ldg(P.n_arc + a);
     const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
-    eps_arrival(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a),
+    eps_arrival<SIMPLE>(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a),
                 static_cast<uint32_t>(ki.y), cstar_key, q_next, q_next_n);
   }
 }
@@ -593,7 +600,7 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
 // good_cut is handed to the next frame's scan, which takes the tokens below it
 // first: its running cutoff tightens early and few arcs that the exact cutoff
 // rejects become candidates.
-template <int THREADS>
+template <int THREADS, bool SIMPLE>
 __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
                                         LaneState &ls, double cstar, double good_cut,
                                         double mid_cut) {
@@ -625,7 +632,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     __syncthreads();
     uint32_t *qc = cur ? q1 : q0, *qx = cur ? q0 : q1;
     for (uint32_t p = tid; p < qn; p += THREADS)
-      expand_eps(P, B, sh, qc[p], cstar_key, cstar, qx, &sh.q_n[cur ^ 1], &eps_count);
+      expand_eps<SIMPLE>(P, B, sh, qc[p], cstar_key, cstar, qx, &sh.q_n[cur ^ 1], &eps_count);
     __syncthreads();
     cur ^= 1;
     ++sweeps;
@@ -689,8 +696,8 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       // Not a token: an arrival recombined while the candidate buffer was full (against
       // the running cutoff) that the exact cutoff rejects.  Its record stays in the
       // block as a hole (state -1, cost +inf) that every reader skips.
-      const bool live =
-          v[u].cost != kEmptyCost && (v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
+      const bool live = v[u].cost != kEmptyCost &&
+                        (SIMPLE || v[u].cost < cstar_key || (v[u].arg >> 63) != 0);
       if (!live) ++dead;
       if (v[u].cost < mid_key) ++below_mid;
       if (write_ok) {
@@ -826,7 +833,7 @@ constexpr int kWindows = KD_WINDOWS;  // 32-arc windows a warp keeps in flight
 //
 // Recombine.  All threads walk the candidate buffer; only candidates with
 // new_weight < C* touch the table, so the table holds exactly the tokens.
-template <int THREADS, bool ROW_SMEM>
+template <int THREADS, bool ROW_SMEM, bool SIMPLE>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
                                        LaneState &ls, const float *row_g, float *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
@@ -1217,6 +1224,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
             if (e < P.ccap) {
               __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
                                             static_cast<uint32_t>(nk >> 32), a, tok_abs));
+            } else if (SIMPLE) {
+              atomicOr(&sh.status, kStatusCandOverflow);
             } else {
               insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
             }
@@ -1248,10 +1257,29 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // (Measured and rejected: taking 2-4 candidates per thread through the dependent
   // loads together -- the recombination gets faster, the other phases of the co-resident
   // lanes slower by as much; claiming the slot with the CAS before any probe load.)
+  double min_stored = inf;  // SIMPLE only
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
     const uint4 c = __ldcs(B.cand + e);
-    const unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
-    if (nk < cstar_key) insert_arc(P, B, sh, c.z, nk, c.w);  // faster-decoder.cc:211, final cutoff
+    unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
+    if (!(nk < cstar_key)) continue;  // faster-decoder.cc:211 / simple-decoder.cc:170, final cutoff
+    if (SIMPLE) {
+      // SimpleDecoder prunes on (cost + w) + ac but stores cost + float(w + ac)
+      // (simple-decoder.cc:168 vs simple-decoder.h:96)
+      const int2 iw = __ldg(P.e_iw + c.z);
+      const float ac = ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1);
+      const double stored = B.a_cost[c.w] + static_cast<double>(__fadd_rn(__int_as_float(iw.y), ac));
+      min_stored = fmin(min_stored, stored);
+      nk = dkey(stored);
+    }
+    insert_arc(P, B, sh, c.z, nk, c.w);
+  }
+  double closure_cutoff = cstar;
+  if (SIMPLE) {
+    // ProcessNonemitting's cutoff: best stored cost + beam (simple-decoder.cc:196-204)
+    double smin;
+    int dummy3;
+    block_min_arg<THREADS>(min_stored, 0, sh, &smin, &dummy3);
+    closure_cutoff = smin + static_cast<double>(P.beam);
   }
   __syncthreads();
   if (tid == 0) {
@@ -1260,7 +1288,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     ls.cyc_expand += t_end - sh.t_mark;
     ls.cyc_scan += t_scan_end - sh.t_mark;
   }
-  return cstar;
+  return closure_cutoff;
 }
 
 // ------------------------------------------------------------------ kernels
@@ -1278,7 +1306,7 @@ __host__ __device__ constexpr size_t advance_smem_fixed() {
 // ROW_SMEM is a template parameter of the kernel (not a run-time branch): the
 // kernel is instruction-cache sensitive (7 lanes per SM run different phases of a
 // ~4500-instruction body), so only the variant in use is instantiated per launch.
-template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
+template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM, bool SIMPLE = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
   constexpr int TT = THREADS * kTileTokens;
   __shared__ Shared sh;
@@ -1336,10 +1364,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params 
       const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
       const int n_in = ls.n_live;
       uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
-      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM>(
+      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM, SIMPLE>(
           P, B, sh, ls, row_g, s_row, t_cost, t_ex, t_beg, t_tab, t_tok, lab_order, bin_start);
       // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
-      lane_closure_and_commit<THREADS>(P, B, sh, ls, cstar,
+      lane_closure_and_commit<THREADS, SIMPLE>(P, B, sh, ls, cstar,
                                        cstar - 0.75 * static_cast<double>(P.beam),
                                        cstar - 0.25 * static_cast<double>(P.beam));
       if (tid == 0) {
@@ -1395,8 +1423,13 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
   }
   __syncthreads();
-  lane_closure_and_commit<THREADS>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */, 0.0,
-                                   0.0);
+  if (P.simple) {
+    // SimpleDecoder::InitDecoding: closure under cutoff 0 + beam (simple-decoder.cc:29-41,196-204)
+    lane_closure_and_commit<THREADS, true>(P, B, sh, ls, static_cast<double>(P.beam), 0.0, 0.0);
+  } else {
+    lane_closure_and_commit<THREADS, false>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */,
+                                            0.0, 0.0);
+  }
   if (tid == 0) {
     ls.status = sh.status;
     ls.st_sweeps = 0;
@@ -1426,12 +1459,21 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
     s_best_tok = kNoIdx;
   }
   __syncthreads();
+  // SimpleDecoder::PruneToks (simple-decoder.cc:251-279) runs after every frame: only
+  // tokens with cost < best + beam exist for ReachedFinal / GetBestPath.  The search
+  // applies the same test when it expands the next frame; here it is applied to the view.
+  const double limit = (P.simple && L->frames_decoded > 0)
+                           ? L->best_cost + static_cast<double>(P.beam)
+                           : inf;
+  const bool pruned_view = P.simple && L->frames_decoded > 0;
   int any = 0;
   for (int i = tid; i < n; i += THREADS) {
     const int s = B.a_state[base + i];
     if (s < 0) continue;  // a hole, not a token
+    const double c = B.a_cost[base + i];
+    if (pruned_view && !(c < limit)) continue;
     float f = __ldg(P.fin + s);
-    if (B.a_cost[base + i] != inf && f != __int_as_float(0x7F800000)) any = 1;
+    if (c != inf && f != __int_as_float(0x7F800000)) any = 1;
   }
   if (any) atomicOr(&s_any_final, 1);
   __syncthreads();
@@ -1442,6 +1484,7 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
     int s = B.a_state[base + i];
     if (s < 0) continue;
     double c = B.a_cost[base + i];
+    if (pruned_view && !(c < limit)) continue;
     double v = is_final ? c + static_cast<double>(__ldg(P.fin + s)) : c;
     bool take = is_final ? (v != inf) : true;
     if (take && (bs < 0 || v < bv || (v == bv && s < bs))) {
@@ -1466,7 +1509,9 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
       L->bp_best_tok = kNoIdx;
       L->bp_best_state = -1;
       L->bp_final_w = 0.f;
+      L->bp_value = inf;
     } else {
+      L->bp_value = rv;
       long long len = 0;
       uint32_t t = s_best_tok;
       while (true) {

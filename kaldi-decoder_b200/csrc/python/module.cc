@@ -20,6 +20,7 @@
 #include "kaldi-decoder_b200/csrc/decodable-itf.h"
 #include "kaldi-decoder_b200/csrc/faster-decoder.h"
 #include "kaldi-decoder_b200/csrc/fst-io.h"
+#include "kaldi-decoder_b200/csrc/simple-decoder.h"
 #include "kaldifst/csrc/remove-eps-local.h"
 #include "kd_capi.h"
 
@@ -233,6 +234,32 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def("advance_decoding", &FasterDecoder::AdvanceDecoding, py::arg("decodable"),
            py::arg("max_num_frames") = -1)
       .def("num_frames_decoded", &FasterDecoder::NumFramesDecoded);
+
+  // ---- SimpleDecoder (kaldi-decoder/python/csrc/simple-decoder.cc:14-44)
+  py::class_<SimpleDecoder>(m, "SimpleDecoder")
+      .def(py::init([](const fst::StdVectorFst &f, float beam) {
+             return std::make_unique<SimpleDecoder>(f, beam);
+           }),
+           py::arg("fst"), py::arg("beam"))
+      .def(py::init([](std::shared_ptr<DeviceGraph> g, float beam, const DeviceConfig &dev) {
+             return std::make_unique<SimpleDecoder>(std::move(g), beam, dev);
+           }),
+           py::arg("graph"), py::arg("beam"), py::arg("device_config") = DeviceConfig())
+      .def("decode", &SimpleDecoder::Decode, py::arg("decodable"))
+      .def("reached_final", &SimpleDecoder::ReachedFinal)
+      .def(
+          "get_best_path",
+          [](SimpleDecoder &self, bool use_final_probs) -> std::pair<bool, fst::Lattice> {
+            fst::Lattice lat;
+            bool ok = self.GetBestPath(&lat, use_final_probs);
+            return std::make_pair(ok, lat);
+          },
+          py::arg("use_final_probs") = true)
+      .def("final_relative_cost", &SimpleDecoder::FinalRelativeCost)
+      .def("init_decoding", &SimpleDecoder::InitDecoding)
+      .def("advance_decoding", &SimpleDecoder::AdvanceDecoding, py::arg("decodable"),
+           py::arg("max_num_frames") = -1)
+      .def("num_frames_decoded", &SimpleDecoder::NumFramesDecoded);
 
   // ---- additive: many lanes per call
   py::class_<BatchFasterDecoder>(m, "BatchFasterDecoder")

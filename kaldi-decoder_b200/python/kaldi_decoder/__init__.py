@@ -5,8 +5,9 @@ __init__.py:1-9) keep their import path, signatures and defaults:
 
     from kaldi_decoder import DecodableCtc, DecodableInterface, FasterDecoder, FasterDecoderOptions
 
-`SimpleDecoder`, `LatticeSimpleDecoder` and `LatticeSimpleDecoderConfig` are not
-part of the accelerated path and are not provided.
+`SimpleDecoder` (beam-only search) runs on the same kernels.
+`LatticeSimpleDecoder` and `LatticeSimpleDecoderConfig` are not part of the
+accelerated path and are not provided.
 
 Additions: `StdVectorFst`, `Lattice`, `get_linear_symbol_sequence` (stand-ins for
 the kaldifst types the reference's bindings exchange -- kaldifst is a separate
@@ -25,6 +26,7 @@ try:
         FasterDecoder,
         FasterDecoderOptions,
         Lattice,
+        SimpleDecoder,
         StdVectorFst,
         device_count,
         get_linear_symbol_sequence,

@@ -19,6 +19,7 @@ LIB_DIR = os.path.normpath(os.path.join(_HERE, "..", "..", "lib"))
 LIB_PATH = os.environ.get("KD_B200_LIB") or os.path.join(LIB_DIR, "libkd_b200.so")
 
 KD_OK = 0
+KD_SEARCH_FASTER, KD_SEARCH_SIMPLE = 0, 1
 KD_MEM_HOST = 0
 KD_MEM_DEVICE = 1
 INT32_MAX = 2**31 - 1
@@ -32,7 +33,7 @@ class KdOptions(C.Structure):
 class KdConfig(C.Structure):
     _fields_ = [("max_lanes", C.c_int32), ("hash_capacity", C.c_int32),
                 ("arena_records", C.c_int64), ("threads_per_lane", C.c_int32),
-                ("chunk_frames", C.c_int32)]
+                ("chunk_frames", C.c_int32), ("search", C.c_int32)]
 
 
 class KdStats(C.Structure):
@@ -53,7 +54,7 @@ EXPORTED = (
     "kd_decoder_best_path_prepare", "kd_decoder_best_path_fetch", "kd_decoder_best_path_view",
     "kd_decoder_best_path",
     "kd_decoder_dump_tokens", "kd_decoder_stats", "kd_decoder_last_advance_info",
-    "kd_decoder_info",
+    "kd_decoder_info", "kd_decoder_final_relative_cost",
 )
 
 _lib = None
@@ -90,6 +91,7 @@ def lib():
         L.kd_decoder_stats.argtypes = [vp, i32, C.POINTER(KdStats)]
         L.kd_decoder_last_advance_info.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
         L.kd_decoder_info.argtypes = [vp, vp]
+        L.kd_decoder_final_relative_cost.argtypes = [vp, i32, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -208,10 +210,10 @@ class LaneDecoder:
 
     def __init__(self, graph: DeviceGraph, opts: KdOptions, max_lanes: int = 1,
                  hash_capacity: int = 0, arena_records: int = 0, threads_per_lane: int = 0,
-                 chunk_frames: int = 0):
+                 chunk_frames: int = 0, search: int = 0):
         self.graph = graph
         cfg = KdConfig(int(max_lanes), int(hash_capacity), int(arena_records),
-                       int(threads_per_lane), int(chunk_frames))
+                       int(threads_per_lane), int(chunk_frames), int(search))
         h = C.c_void_p()
         _check(lib().kd_decoder_create(graph.h, C.byref(opts), C.byref(cfg), C.byref(h)))
         self.h = h
@@ -306,6 +308,11 @@ class LaneDecoder:
             _check(lib().kd_decoder_dump_tokens(self.h, int(lane), n.value, st.ctypes.data,
                                                 co.ctypes.data, C.byref(n)))
         return st, co
+
+    def final_relative_cost(self, lane: int = 0) -> float:
+        v = C.c_float(0)
+        _check(lib().kd_decoder_final_relative_cost(self.h, int(lane), C.byref(v)))
+        return v.value
 
     def stats(self, lane: int = -1) -> dict:
         s = KdStats()

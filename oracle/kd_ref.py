@@ -62,6 +62,21 @@ def lib():
             C.c_float, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_int, C.c_int32,
             C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p]
+        if hasattr(L, "kdref_simple_create"):
+            L.kdref_simple_create.restype = C.c_void_p
+            L.kdref_simple_create.argtypes = [C.c_void_p, C.c_float]
+            L.kdref_simple_destroy.argtypes = [C.c_void_p]
+            L.kdref_simple_init.argtypes = [C.c_void_p]
+            L.kdref_simple_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                               C.c_int32, C.c_int32]
+            L.kdref_simple_num_frames_decoded.argtypes = [C.c_void_p]
+            L.kdref_simple_num_frames_decoded.restype = C.c_int32
+            L.kdref_simple_reached_final.argtypes = [C.c_void_p]
+            L.kdref_simple_final_relative_cost.argtypes = [C.c_void_p]
+            L.kdref_simple_final_relative_cost.restype = C.c_float
+            L.kdref_simple_best_path.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.kdref_simple_best_path.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -183,6 +198,62 @@ class RefDecoder:
             n = lib().kdref_decoder_best_path(self.h, int(use_final_probs), cap, il.ctypes.data,
                                               ol.ctypes.data, gw.ctypes.data, aw.ctypes.data,
                                               f2.ctypes.data)
+            if n == -2:
+                raise RuntimeError(_err())
+            if n == -1:
+                e = np.empty(0, np.int32)
+                return BestPath(False, e, e, np.empty(0, np.float32), np.empty(0, np.float32), f2)
+            if n <= cap:
+                return BestPath(True, il[:n].copy(), ol[:n].copy(), gw[:n].copy(), aw[:n].copy(), f2)
+            cap = int(n)
+
+
+class RefSimpleDecoder:
+    """The reference SimpleDecoder (simple-decoder.cc, unmodified) behind the harness's C-ABI."""
+
+    def __init__(self, graph: RefGraph, beam: float):
+        self.graph = graph
+        self.h = lib().kdref_simple_create(graph.h, float(beam))
+        if not self.h:
+            raise RuntimeError(_err())
+        self._keep = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().kdref_simple_destroy(self.h)
+            self.h = None
+
+    def init_decoding(self):
+        if lib().kdref_simple_init(self.h) != 0:
+            raise RuntimeError(_err())
+
+    def advance_decoding(self, logp: np.ndarray, offset: int = 0, max_num_frames: int = -1):
+        logp = np.ascontiguousarray(logp, dtype=np.float32)
+        self._keep = logp
+        if lib().kdref_simple_advance(self.h, logp.ctypes.data, logp.shape[0], logp.shape[1],
+                                      offset, max_num_frames) != 0:
+            raise RuntimeError(_err())
+
+    def num_frames_decoded(self) -> int:
+        return lib().kdref_simple_num_frames_decoded(self.h)
+
+    def reached_final(self) -> bool:
+        return bool(lib().kdref_simple_reached_final(self.h))
+
+    def final_relative_cost(self) -> float:
+        return float(lib().kdref_simple_final_relative_cost(self.h))
+
+    def get_best_path(self, use_final_probs: bool = True) -> BestPath:
+        cap = 4 * max(1, self.num_frames_decoded()) + 64
+        while True:
+            il = np.empty(cap, np.int32)
+            ol = np.empty(cap, np.int32)
+            gw = np.empty(cap, np.float32)
+            aw = np.empty(cap, np.float32)
+            f2 = np.zeros(2, np.float32)
+            n = lib().kdref_simple_best_path(self.h, int(use_final_probs), cap, il.ctypes.data,
+                                             ol.ctypes.data, gw.ctypes.data, aw.ctypes.data,
+                                             f2.ctypes.data)
             if n == -2:
                 raise RuntimeError(_err())
             if n == -1:

@@ -25,7 +25,10 @@
 #include <thread>
 #include <vector>
 
+#include <unordered_map>
+
 #include "kaldi-decoder/csrc/faster-decoder.h"
+#include "kaldi-decoder/csrc/simple-decoder.h"
 
 namespace {
 
@@ -299,6 +302,76 @@ double kdref_decode_batch(void *graph, const float *logp, int32_t n_utts,
     return -1.0;
   }
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---------------------------------------------------------------- SimpleDecoder
+// (kaldi-decoder/csrc/simple-decoder.{h,cc}, unmodified)
+
+struct SimpleHandle {
+  const Graph *graph;
+  std::unique_ptr<kaldi_decoder::SimpleDecoder> dec;
+};
+
+void *kdref_simple_create(void *graph, float beam) {
+  try {
+    auto *g = static_cast<Graph *>(graph);
+    auto *h = new SimpleHandle;
+    h->graph = g;
+    h->dec.reset(new kaldi_decoder::SimpleDecoder(*g->fst, beam));
+    return h;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return nullptr;
+  }
+}
+
+void kdref_simple_destroy(void *d) { delete static_cast<SimpleHandle *>(d); }
+
+int kdref_simple_init(void *d) {
+  try {
+    static_cast<SimpleHandle *>(d)->dec->InitDecoding();
+    return 0;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+int kdref_simple_advance(void *d, const float *logp, int32_t rows, int32_t cols, int32_t offset,
+                         int32_t max_num_frames) {
+  try {
+    PtrDecodable dec(logp, rows, cols, offset);
+    static_cast<SimpleHandle *>(d)->dec->AdvanceDecoding(&dec, max_num_frames);
+    return 0;
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -1;
+  }
+}
+
+int32_t kdref_simple_num_frames_decoded(void *d) {
+  return static_cast<SimpleHandle *>(d)->dec->NumFramesDecoded();
+}
+
+int kdref_simple_reached_final(void *d) {
+  return static_cast<SimpleHandle *>(d)->dec->ReachedFinal() ? 1 : 0;
+}
+
+float kdref_simple_final_relative_cost(void *d) {
+  return static_cast<SimpleHandle *>(d)->dec->FinalRelativeCost();
+}
+
+int64_t kdref_simple_best_path(void *d, int use_final_probs, int64_t cap, int32_t *il,
+                               int32_t *ol, float *graph, float *ac, float *final2) {
+  try {
+    fst::Lattice lat;
+    bool ok = static_cast<SimpleHandle *>(d)->dec->GetBestPath(&lat, use_final_probs != 0);
+    if (!ok) return -1;
+    return FlattenLinear(lat, cap, il, ol, graph, ac, final2);
+  } catch (const std::exception &e) {
+    g_error = e.what();
+    return -2;
+  }
 }
 
 }  // extern "C"
