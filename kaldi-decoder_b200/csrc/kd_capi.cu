@@ -58,7 +58,7 @@ struct kd_graph {
   unsigned char *blob = nullptr;
   size_t blob_bytes = 0;
   int64_t num_label_tables = 0;
-  uint16_t *labtab = nullptr;  // [num_label_tables][max_ilabel]: ilabel-1 -> arc offset in its state
+  int2 *labtab = nullptr;  // [num_label_tables][max_ilabel]: ilabel-1 -> {weight bits, arc offset in its state or -1}
   int4 *st = nullptr;          // 2 x int4 per state
   int2 *e_iw = nullptr;
   int2 *e_no = nullptr;
@@ -366,23 +366,24 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
     n_eps += nn;
   }
   // Label tables: for states with many emitting arcs and distinct ilabels, a row
-  // ilabel-1 -> offset of that arc within the state.  A token whose slack
+  // ilabel-1 -> (weight, offset) of that arc within the state: one 8-byte load gives a
+  // looked-up arc's weight, the arc record itself is only read for candidates.  A token whose slack
   // (cutoff - cost - smallest weight) only admits the few best labels of the frame
   // looks those labels up instead of scanning all its arcs.
-  std::vector<uint16_t> labtab;
+  std::vector<int2> labtab;
   int64_t n_tab = 0;
   if (max_il > 0 && max_il <= 65535 && getenv("KD_B200_NO_LABEL_TABLES") == nullptr) {
     std::vector<std::pair<int32_t, int32_t>> cands;  // (emit count, state)
     for (int32_t s = 0; s < num_states; ++s) {
       const int ne = st[2 * static_cast<size_t>(s)].y;
-      if (ne >= kd::kLabelTableMinDegree && ne < 65535) cands.emplace_back(ne, s);
+      if (ne >= kd::kLabelTableMinDegree) cands.emplace_back(ne, s);
     }
     std::sort(cands.begin(), cands.end(), [](const std::pair<int32_t, int32_t> &a,
                                              const std::pair<int32_t, int32_t> &b) {
       return a.first != b.first ? a.first > b.first : a.second < b.second;
     });
-    const size_t row_bytes = static_cast<size_t>(max_il) * sizeof(uint16_t);
-    const size_t budget = std::max<size_t>(64u << 20, static_cast<size_t>(n_emit) * 4);
+    const size_t row_bytes = static_cast<size_t>(max_il) * sizeof(int2);
+    const size_t budget = std::max<size_t>(256u << 20, static_cast<size_t>(n_emit) * 16);
     std::vector<int32_t> stamp(static_cast<size_t>(max_il) + 1, -1);
     for (const auto &c : cands) {
       if ((static_cast<size_t>(n_tab) + 1) * row_bytes > budget) break;
@@ -394,12 +395,14 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
         stamp[ilabel[a]] = s;
       }
       if (!distinct) continue;
-      labtab.resize((static_cast<size_t>(n_tab) + 1) * max_il, 0xFFFFu);
-      uint16_t *row = labtab.data() + static_cast<size_t>(n_tab) * max_il;
-      uint16_t off = 0;
+      labtab.resize((static_cast<size_t>(n_tab) + 1) * max_il, make_int2(0, -1));
+      int2 *row = labtab.data() + static_cast<size_t>(n_tab) * max_il;
+      int32_t off = 0;
       for (int64_t a = row_offsets[s]; a < row_offsets[s + 1]; ++a) {
         if (ilabel[a] == 0) continue;
-        row[ilabel[a] - 1] = off++;
+        int wbits;
+        memcpy(&wbits, &weight[a], 4);
+        row[ilabel[a] - 1] = make_int2(wbits, off++);
       }
       st[2 * static_cast<size_t>(s) + 1].x = static_cast<int>(n_tab);
       ++n_tab;
@@ -441,7 +444,7 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   const size_t b_iw = round256(eiw.size() * sizeof(int2)), b_st = round256(st.size() * sizeof(int4)),
                b_no = round256(eno.size() * sizeof(int2)), b_na = round256(na.size() * sizeof(int4)),
                b_fin = round256(static_cast<size_t>(num_states) * sizeof(float)),
-               b_tab = round256(labtab.size() * sizeof(uint16_t));
+               b_tab = round256(labtab.size() * sizeof(int2));
   g->blob_bytes = b_iw + b_st + b_no + b_na + b_fin + b_tab;
   g->num_label_tables = n_tab;
   if ((rc = DevAlloc(&g->blob, g->blob_bytes))) {
@@ -453,9 +456,9 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   g->e_no = reinterpret_cast<int2 *>(g->blob + b_iw + b_st);
   g->n_arc = reinterpret_cast<int4 *>(g->blob + b_iw + b_st + b_no);
   g->fin = reinterpret_cast<float *>(g->blob + b_iw + b_st + b_no + b_na);
-  g->labtab = reinterpret_cast<uint16_t *>(g->blob + b_iw + b_st + b_no + b_na + b_fin);
+  g->labtab = reinterpret_cast<int2 *>(g->blob + b_iw + b_st + b_no + b_na + b_fin);
   if (!labtab.empty())
-    KD_CUDA(cudaMemcpy(g->labtab, labtab.data(), labtab.size() * sizeof(uint16_t),
+    KD_CUDA(cudaMemcpy(g->labtab, labtab.data(), labtab.size() * sizeof(int2),
                        cudaMemcpyHostToDevice));
   KD_CUDA(cudaMemcpy(g->st, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice));
   if (!eiw.empty()) {

@@ -127,7 +127,7 @@ struct Params {
   // their own; (nextstate, olabel) are read for admitted arcs only.
   const int4 *st;      // [2S] {emit_begin, emit_count, eps_begin, eps_count},
                        //      {label-table row or -1, smallest emitting weight bits, 0, 0}
-  const uint16_t *labtab;  // [rows][lab_stride]: ilabel-1 -> arc offset within the state, 0xFFFF none
+  const int2 *labtab;  // [rows][lab_stride]: ilabel-1 -> {weight bits, arc offset within the state or -1}
   int32_t lab_stride;
   int32_t simple;      // 1: SimpleDecoder semantics (simple-decoder.cc), else FasterDecoder
   const int2 *e_iw;    // [Ee] {ilabel, weight bits}
@@ -798,10 +798,6 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
 }
 
 
-#ifndef KD_WINDOWS
-#define KD_WINDOWS 1
-#endif
-constexpr int kWindows = KD_WINDOWS;  // 32-arc windows a warp keeps in flight
 
 // faster-decoder.cc:155-241 for one lane-frame.  Returns C*.
 //
@@ -839,7 +835,6 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
                                        int32_t *t_tab, uint32_t *t_tok, uint16_t *lab_order,
                                        uint16_t *bin_start) {
-  constexpr int U = kWindows;
   constexpr int KT = kTileTokens;
   constexpr int TT = THREADS * KT;
   constexpr int NW = THREADS / 32;
@@ -954,11 +949,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     if (sh.order_ok != 0 && sb.x >= 0) {
       if (tid < P.cols) {
         const uint32_t lab = lab_order[tid];
-        const uint32_t off = __ldg(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
-        if (off != 0xFFFFu) {
-          const int2 iw = __ldg(P.e_iw + st.x + off);
-          seed = (widen(__int_as_float(iw.y)) + ls.best_cost) + widen(s_row[lab - 1]);
-        }
+        const int2 ent = __ldg(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
+        if (ent.y >= 0)
+          seed = (widen(__int_as_float(ent.x)) + ls.best_cost) + widen(s_row[lab - 1]);
       }
     } else {
 #pragma unroll 1
@@ -1128,12 +1121,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       sh.acc_items += n_flat;
     }
     __syncthreads();
-    // flat item loop: steps of 32 * U items are dealt round-robin to the warps, so
-    // all warps start at the front of the flat space.
+    // flat item loop: 32-item windows are dealt round-robin to the warps, so all warps
+    // start at the front of the flat space.  (One window per step: keeping several in
+    // flight made the loop body, and with it the kernel, too large for the instruction
+    // cache -- 100 -> 89 ms per launch going from 4 windows to 1.)
     {
       const uint32_t jw1 = n_flat;
 #pragma unroll 1
-      for (uint32_t jb = warp * (32 * U); jb < jw1; jb += NW * 32 * U) {
+      for (uint32_t jb = warp * 32; jb < jw1; jb += NW * 32) {
         // compacted token owning item jb = largest t with t_ex[t] <= jb: 32-ary search,
         // every lane probes one position per level (t_ex[0] = 0 <= jb always)
         uint32_t t_lo = 0;
@@ -1143,99 +1138,70 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
           const bool le = pos < n_comp && t_ex[pos] <= jb;
           t_lo += (__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u) * stride;
         }
-        int2 iw[U];
-        uint32_t tt[U];   // compacted token of the item, kNoIdx if none
-        uint32_t aa[U];   // emitting arc index of the item, kNoIdx if none
-        uint32_t lk[U];   // lookup items: label-table value (fetched in stage 1)
-        // stage 1: item -> token; lookup items fetch their label-table entry
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const uint32_t j0 = jb + 32 * u;
-          const uint32_t j = j0 + lane;
-          tt[u] = kNoIdx;
-          aa[u] = kNoIdx;
-          lk[u] = 0xFFFFu;
-          if (j0 < jw1) {  // warp-uniform
-            // boundaries (first item index) of the 32 tokens after t_lo
-            const uint32_t bnd = t_ex[min(t_lo + 1 + lane, n_comp)];
-            const uint32_t p = bnd - j0;  // >= 1: token t_lo owns item j0
-            const uint32_t mask = __reduce_or_sync(0xFFFFFFFFu, p < 32 ? (1u << p) : 0u);
-            const bool edge = __any_sync(0xFFFFFFFFu, p == 32);
-            const uint32_t t = t_lo + __popc(mask & ((2u << lane) - 1u));
-            if (j < jw1) {
-              tt[u] = t;
-              const uint32_t b = t_beg[t];
-              const uint32_t k = j - t_ex[t];
-              if (b & kLookupFlag) {
-                const uint32_t lab = lab_order[k];
-                lk[u] = __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
-                aa[u] = b & ~kLookupFlag;  // base; the offset is added in stage 2
-              } else {
-                aa[u] = b + k;
+        // item -> token: bit mask of the token boundaries (first item index of the 32
+        // tokens after t_lo) that fall inside the window
+        int2 iw = make_int2(1, 0);  // {ilabel, weight bits} of the item's arc
+        uint32_t tt = kNoIdx;       // compacted token of the item, kNoIdx if none
+        uint32_t aa = kNoIdx;       // emitting arc index of the item
+        {
+          const uint32_t j = jb + lane;
+          const uint32_t bnd = t_ex[min(t_lo + 1 + lane, n_comp)];
+          const uint32_t p = bnd - jb;  // >= 1: token t_lo owns item jb
+          const uint32_t mask = __reduce_or_sync(0xFFFFFFFFu, p < 32 ? (1u << p) : 0u);
+          const uint32_t t = t_lo + __popc(mask & ((2u << lane) - 1u));
+          if (j < jw1) {
+            const uint32_t b = t_beg[t];
+            const uint32_t k = j - t_ex[t];
+            if (b & kLookupFlag) {
+              // the k-th best label of the frame, looked up in the state's label table:
+              // one load gives the arc's weight and its offset within the state
+              const uint32_t lab = lab_order[k];
+              const int2 ent =
+                  __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
+              if (ent.y >= 0) {  // else: the state has no arc with this label
+                tt = t;
+                aa = (b & ~kLookupFlag) + static_cast<uint32_t>(ent.y);
+                iw = make_int2(static_cast<int>(lab), ent.x);
               }
+            } else {
+              tt = t;
+              aa = b + k;
+              iw = __ldg(P.e_iw + aa);
             }
-            t_lo += __popc(mask) + (edge ? 1u : 0u);
-          }
-        }
-        // stage 2: arc loads
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          iw[u] = make_int2(1, 0);
-          if (tt[u] != kNoIdx) {
-            if (t_beg[tt[u]] & kLookupFlag) {
-              if (lk[u] == 0xFFFFu) {
-                tt[u] = kNoIdx;  // the state has no arc with this label
-                aa[u] = kNoIdx;
-              } else {
-                aa[u] += lk[u];
-              }
-            }
-            if (aa[u] != kNoIdx) iw[u] = __ldg(P.e_iw + aa[u]);
           }
         }
         const double cut_d = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
-        double nw[U];
-        uint32_t adm = 0;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const double ac = widen(ROW_SMEM ? s_row[iw[u].x - 1] : -__ldg(row_g + iw[u].x - 1));
-          const double tcst = t_cost[min(tt[u], static_cast<uint32_t>(TT - 1))];
-          nw[u] = (widen(__int_as_float(iw[u].y)) + tcst) + ac;
-          // faster-decoder.cc:211 against the running cutoff
-          if (tt[u] != kNoIdx && nw[u] < cut_d) adm |= 1u << u;
-        }
+        const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
+        const double tcst = t_cost[min(tt, static_cast<uint32_t>(TT - 1))];
+        const double nw = (widen(__int_as_float(iw.y)) + tcst) + ac;
+        // faster-decoder.cc:211 against the running cutoff
+        const bool is_cand = tt != kNoIdx && nw < cut_d;
         // Candidates are appended warp-aggregated: about a third of the looked-up arcs
         // pass the filter, and one shared-memory atomic per candidate on the single
-        // counter serialised the whole CTA (the per-step cost was dominated by it).
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const bool is_cand = (adm >> u) & 1u;
-          const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
-          if (cmask == 0) continue;  // warp-uniform
-          uint32_t cbase = 0;
-          if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
-          cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
-          if (is_cand) {
-            const uint32_t t = tt[u];
-            const uint32_t a = aa[u];
-            const uint32_t tok_abs = base + t_tok[t];
-            const unsigned long long nk = dkey(nw[u]);
-            const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
-            if (e < P.ccap) {
-              __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
-                                            static_cast<uint32_t>(nk >> 32), a, tok_abs));
-            } else if (SIMPLE) {
-              atomicOr(&sh.status, kStatusCandOverflow);
-            } else {
-              insert_arc(P, B, sh, a, nk, tok_abs);  // buffer full: recombine now
-            }
-            if (nw[u] < my_min) {
-              my_min = nw[u];
-              // faster-decoder.cc:215-217
-              const uint32_t fk = fkey(__double2float_ru(nw[u] + ab));
-              if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
-                atomicMin(&sh.cut_fkey, fk);
-            }
+        // counter serialised the whole CTA.
+        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+        if (cmask == 0) continue;  // warp-uniform
+        uint32_t cbase = 0;
+        if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
+        cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+        if (is_cand) {
+          const uint32_t tok_abs = base + t_tok[tt];
+          const unsigned long long nk = dkey(nw);
+          const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
+          if (e < P.ccap) {
+            __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
+                                          static_cast<uint32_t>(nk >> 32), aa, tok_abs));
+          } else if (SIMPLE) {
+            atomicOr(&sh.status, kStatusCandOverflow);
+          } else {
+            insert_arc(P, B, sh, aa, nk, tok_abs);  // buffer full: recombine now
+          }
+          if (nw < my_min) {
+            my_min = nw;
+            // faster-decoder.cc:215-217
+            const uint32_t fk = fkey(__double2float_ru(nw + ab));
+            if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
+              atomicMin(&sh.cut_fkey, fk);
           }
         }
       }
