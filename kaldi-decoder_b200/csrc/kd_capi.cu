@@ -242,7 +242,9 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
     case 160:
       return LaunchAdvanceT<160, 7>(d, P, n_items, s);
     case 192:
-      return LaunchAdvanceT<192, 5>(d, P, n_items, s);
+      return LaunchAdvanceT<192, 7>(d, P, n_items, s);
+    case 224:
+      return LaunchAdvanceT<224, 7>(d, P, n_items, s);
     case 256:
       return LaunchAdvanceT<256, 3>(d, P, n_items, s);
     case 512:
@@ -528,7 +530,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->lcap = p2 / 2;
   d->qcap = p2;
   d->ccap = p2 / 4;
-  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 && c.threads_per_lane != 192 &&
+  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 && c.threads_per_lane != 192 && c.threads_per_lane != 224 &&
       c.threads_per_lane != 256 && c.threads_per_lane != 512) {
     delete d;
     return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 256 or 512");

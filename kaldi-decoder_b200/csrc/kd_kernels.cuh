@@ -1271,9 +1271,19 @@ __host__ __device__ constexpr size_t advance_smem_fixed() {
 
 // ROW_SMEM is a template parameter of the kernel (not a run-time branch): the
 // kernel is instruction-cache sensitive (7 lanes per SM run different phases of a
-// ~4500-instruction body), so only the variant in use is instantiated per launch.
+// ~3500-instruction body), so only the variant in use is instantiated per launch.
+// Registers per thread such that MIN_BLOCKS lanes of THREADS threads fit an SM: the register
+// file is four 16 K-register partitions (one per scheduler), a warp's registers come out
+// of one of them, in units of 8 per thread.
+constexpr int advance_max_regs(int threads, int min_blocks) {
+  const int warps_per_partition = (min_blocks * (threads / 32) + 3) / 4;
+  const int r = (16384 / warps_per_partition / 32) / 8 * 8;
+  return r > 255 ? 255 : r;
+}
+
 template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM, bool SIMPLE = false>
-__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) kd_advance_kernel(Params P) {
+__global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS, MIN_BLOCKS))
+    kd_advance_kernel(Params P) {
   constexpr int TT = THREADS * kTileTokens;
   __shared__ Shared sh;
   __shared__ LaneState ls;
