@@ -239,6 +239,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t *total) 
 struct Shared {
   double red_d[32];
   int red_i[32];
+  unsigned long long red_k[2][16];  // block_min: per-warp minima, two buffers used alternately
   uint32_t hist[256];
   uint32_t warp_sums[32];
   long long t_mark;
@@ -263,10 +264,35 @@ struct Shared {
   int32_t rows_ready;
 };
 
+// min over the block of a double, value only: ordered 64-bit keys, the warp minimum by
+// two 32-bit REDUX.MIN (high words, then low words among the lanes holding the minimal
+// high word), one barrier, every thread folds the per-warp minima itself.  `phase` (0/1)
+// selects the buffer; consecutive calls alternate, which makes the single barrier enough
+// (a buffer is rewritten two calls later, behind the barrier of the call in between).
+template <int THREADS>
+__device__ __forceinline__ double block_min(double v, Shared &sh, int phase) {
+  constexpr int NW = THREADS / 32;
+  const unsigned long long k = dkey(v);
+  const uint32_t hi = static_cast<uint32_t>(k >> 32);
+  const uint32_t mh = __reduce_min_sync(0xFFFFFFFFu, hi);
+  const uint32_t ml =
+      __reduce_min_sync(0xFFFFFFFFu, hi == mh ? static_cast<uint32_t>(k) : 0xFFFFFFFFu);
+  if ((threadIdx.x & 31) == 0)
+    sh.red_k[phase][threadIdx.x >> 5] = (static_cast<unsigned long long>(mh) << 32) | ml;
+  __syncthreads();
+  unsigned long long m = sh.red_k[phase][0];
+#pragma unroll
+  for (int w = 1; w < NW; ++w) {
+    const unsigned long long o = sh.red_k[phase][w];
+    m = o < m ? o : m;
+  }
+  return dunkey(m);
+}
+
 // min over the block of (v, idx); ties -> lowest idx.  All threads get it.
 template <int THREADS>
 #ifndef KD_INLINE_MIN
-#define KD_INLINE_MIN __noinline__
+#define KD_INLINE_MIN __forceinline__
 #endif
 __device__ KD_INLINE_MIN void block_min_arg(double v, int idx, Shared &sh, double *out_v,
                                               int *out_i) {
@@ -880,10 +906,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     static_assert(6 * TT >= kOrderBins, "tile arrays too small to hold the label histogram");
 #pragma unroll 1
     for (int b = tid; b < kOrderBins; b += THREADS) hist[b] = 0;
-    double dmin;
-    int dummy;
-    block_min_arg<THREADS>(static_cast<double>(amin), 0, sh, &dmin, &dummy);
-    amin = static_cast<float>(dmin);
+    amin = static_cast<float>(block_min<THREADS>(static_cast<double>(amin), sh, 0));
     // (these loops touch shared memory only: not unrolled, the kernel is short of
     // instruction cache, not of latency hiding here)
 #pragma unroll 1
@@ -964,9 +987,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     }
   }
   {
-    double smin;
-    int dummy;
-    block_min_arg<THREADS>(seed, 0, sh, &smin, &dummy);
+    const double smin = block_min<THREADS>(seed, sh, 1);
     if (tid == 0) sh.cut_fkey = fkey(__double2float_ru(smin + ab));
     __syncthreads();
   }
@@ -1212,9 +1233,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   }
   const long long t_scan_end = clock64();
   // ---------------------------------------------------------------- exact cutoff
-  double bmin;
-  int dummy2;
-  block_min_arg<THREADS>(fmin(my_min, seed), 0, sh, &bmin, &dummy2);
+  const double bmin = block_min<THREADS>(fmin(my_min, seed), sh, 0);
   const double cstar = bmin + ab;
   const unsigned long long cstar_key = dkey(cstar);
   // ---------------------------------------------------------------- recombine
@@ -1242,9 +1261,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   double closure_cutoff = cstar;
   if (SIMPLE) {
     // ProcessNonemitting's cutoff: best stored cost + beam (simple-decoder.cc:196-204)
-    double smin;
-    int dummy3;
-    block_min_arg<THREADS>(min_stored, 0, sh, &smin, &dummy3);
+    const double smin = block_min<THREADS>(min_stored, sh, 1);
     closure_cutoff = smin + static_cast<double>(P.beam);
   }
   __syncthreads();
