@@ -89,6 +89,7 @@ struct __align__(16) LaneState {
   int32_t frames_decoded;  // num_frames_decoded_; -1 before InitDecoding
   int32_t status;          // kStatus* bits; non-zero = lane unusable until init
   int32_t best_idx;        // index (in the current token block) of a best token
+  int32_t best_state;      // its state (-1 if none)
   int32_t n_live;          // tokens alive (the reference's toks_ list length)
   int32_t n_front;         // tokens below good_cut; the first kFrontCap of them are in the front list
   int32_t n_mid;           // tokens below mid_cut
@@ -565,13 +566,21 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
                                             uint32_t arc, uint32_t src_number,
                                             unsigned long long cstar_key, uint32_t *q_next,
                                             uint32_t *q_next_n) {
-  const uint32_t h =
-      table_slot(P, B, sh, static_cast<int32_t>(dst_word & ~kEpsFlag), nullptr, nullptr);
-  if (h == kNoIdx) return;
+  // key and value of the first probed slot are fetched together (one sector, one round trip)
+  const int32_t state = static_cast<int32_t>(dst_word & ~kEpsFlag);
+  const uint32_t h0 = table_hash(P, state);
+  const int32_t k0 = __ldcg(&B.table[h0].key);
+  HVal cur = ld_hval(&B.table[h0].val);
+  uint32_t h = h0;
+  if (k0 != state) {
+    h = table_slot_from(P, B, sh, state, h0, k0, nullptr, nullptr);
+    if (h == kNoIdx) return;
+    // a freshly claimed slot holds the empty value; a slot found further along is re-read
+    if (h != h0 || k0 != kEmptyKey) cur = ld_hval(&B.table[h].val);
+  }
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_number;
-  HVal cur = ld_hval(&B.table[h].val);
   while (true) {
     const bool cur_is_eps = (cur.arg >> 63) != 0;
     // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
@@ -600,10 +609,11 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
                                            double cstar, uint32_t *q_next, uint32_t *q_next_n,
                                            uint32_t *eps_count) {
   const HVal v = ld_hval(&B.table[slot].val);
+  // {state, number}: same sector as the value, requested together with it
+  const int2 ki = __ldcg(reinterpret_cast<const int2 *>(&B.table[slot].key));
   const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(SIMPLE || v.cost < cstar_key || is_eps)) return;
-  const int2 ki = __ldcg(reinterpret_cast<const int2 *>(&B.table[slot].key));  // {state, number}
   const int4 st = __ldg(P.st + 2 * static_cast<size_t>(ki.x));
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
@@ -678,6 +688,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   const bool write_ok = (sh.status & kStatusArenaOverflow) == 0;
   double my_min = inf;
   int my_arg = -1;
+  int32_t my_state = -1;
   uint32_t dead = 0, below_mid = 0;
   for (uint32_t p0 = 0; p0 < m; p0 += THREADS * 4) {
     uint32_t h[4];
@@ -738,6 +749,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
         if (live && c < my_min) {
           my_min = c;
           my_arg = static_cast<int>(idx);
+          my_state = key[u];
         }
       }
       ulonglong2 e;
@@ -750,6 +762,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   double bmin;
   int barg;
   block_min_arg<THREADS>(my_min, my_arg, sh, &bmin, &barg);
+  if (barg >= 0 && my_arg == barg) ls.best_state = my_state;  // one thread: token numbers are unique
   // accumulate counters
   eps_count = __reduce_add_sync(0xFFFFFFFFu, eps_count);
   if ((tid & 31) == 0 && eps_count) atomicAdd(&sh.acc_eps, eps_count);
@@ -775,6 +788,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.n_live = 0;
       ls.best_cost = inf;
       ls.best_idx = -1;
+      ls.best_state = -1;
     }
     ls.st_sweeps += sweeps;
     ls.st_claimed += m;
@@ -878,6 +892,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // the log-prob row of this frame -> shared memory (decodable-ctc.cc:22-29),
   // already negated (faster-decoder.cc:209); widened to fp64 where it is used.
   // (Shared memory is kept small on purpose: what it does not take is L1.)
+  // the best token's state record is needed for the seed below: requested first, it
+  // arrives while the row is staged and the labels are ordered
+  int4 seed_sa = make_int4(0, 0, 0, 0), seed_sb = make_int4(-1, 0, 0, 0);
+  if (n > 0 && ls.best_state >= 0) {
+    seed_sa = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state));
+    seed_sb = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state) + 1);
+  }
   float amin = __int_as_float(0x7F800000);  // smallest acoustic cost of the frame (ROW_SMEM)
   if (ROW_SMEM) {
     for (int i = tid; i < P.cols; i += THREADS) {
@@ -966,9 +987,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // only looks up the THREADS labels with the best acoustic cost.
   double seed = inf;
   if (n > 0 && ls.best_cost < wc) {
-    const int32_t bs = state[ls.best_idx];
-    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(bs));
-    const int4 sb = __ldg(P.st + 2 * static_cast<size_t>(bs) + 1);
+    const int4 st = seed_sa;
+    const int4 sb = seed_sb;
     if (sh.order_ok != 0 && sb.x >= 0) {
       if (tid < P.cols) {
         const uint32_t lab = lab_order[tid];
@@ -1400,6 +1420,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     z.frames_decoded = 0;
     z.best_cost = __longlong_as_double(0x7FF0000000000000ll);
     z.best_idx = -1;
+    z.best_state = -1;
     ls = z;
     sh.status = 0;
     sh.list_n = 0;
