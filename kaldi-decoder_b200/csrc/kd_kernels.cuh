@@ -60,10 +60,7 @@ constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
 constexpr int kOrderBins = 512;           // buckets of the per-frame label order (1/16 wide)
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
-#ifndef KD_TILE_TOKENS
-#define KD_TILE_TOKENS 2
-#endif
-constexpr int kTileTokens = KD_TILE_TOKENS;            // tokens per thread in one scan tile
+constexpr int kTileTokens = 2;            // tokens per thread in one scan tile
 constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
@@ -292,10 +289,7 @@ __device__ __forceinline__ double block_min(double v, Shared &sh, int phase) {
 
 // min over the block of (v, idx); ties -> lowest idx.  All threads get it.
 template <int THREADS>
-#ifndef KD_INLINE_MIN
-#define KD_INLINE_MIN __forceinline__
-#endif
-__device__ KD_INLINE_MIN void block_min_arg(double v, int idx, Shared &sh, double *out_v,
+__device__ __forceinline__ void block_min_arg(double v, int idx, Shared &sh, double *out_v,
                                               int *out_i) {
   constexpr int NW = THREADS / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -843,24 +837,23 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
 //
 // Three steps: scan -> exact cutoff -> recombine.
 //
-// Scan.  The tokens are taken a tile (4 per thread) at a time.  Tokens that
-// will be expanded (cost < weight_cutoff, at least one emitting arc) are
-// compacted into shared memory together with the exclusive prefix sum of their
-// emitting out-degrees, so the tile's arcs form one flat index space.  Each
-// warp owns a contiguous slice of it and walks it 32 arcs (one coalesced
-// window) at a time, kWindows windows in flight.  The token owning each arc of
-// a window comes from a bit mask of the token boundaries falling inside the
-// window (one shared-memory load, one warp OR-reduction, one popc).
-// new_weight = (w + cost) + ac is computed for all arcs of a step first
-// (straight-line code).  ~97% of the arcs fail the pruning test and cost
-// nothing more.  The others are only *candidates*: the test is made against a
-// running cutoff (the reference's next_weight_cutoff, faster-decoder.cc:172-217)
-// kept in shared memory as a float rounded UP and lowered with one native
-// 32-bit atomicMin; it is looser than the final cutoff.  Candidates are
-// appended to a per-lane buffer, not recombined: recombining them on the spot
-// makes a warp wait for one lane's table round trips, and fills the table
-// (and L2) with arrivals that the final cutoff rejects -- 3x more slots claimed
-// than tokens kept (profiles/r1_v5_ncu_summary.txt).
+// Scan.  Two passes over the token block (front list first, then the rest), the
+// tokens taken a chunk (kTileTokens per thread) at a time.  Tokens that will be
+// expanded (cost < weight_cutoff, at least one emitting arc) are compacted into
+// shared memory together with the exclusive prefix sum of their work items -- all
+// their emitting arcs, or just the frame's best labels looked up in the state's label
+// table -- so the chunk's items form one flat index space.  The warps walk it one
+// 32-item window at a time, round-robin.  The token owning each item of a window
+// comes from a bit mask of the token boundaries falling inside the window (one
+// shared-memory load, one warp OR-reduction, one popc).  new_weight = (w + cost) + ac.
+// Most items fail the pruning test and cost nothing more.  The others are only
+// *candidates*: the test is made against a running cutoff (the reference's
+// next_weight_cutoff, faster-decoder.cc:172-217) kept in shared memory as a float
+// rounded UP and lowered with one native 32-bit atomicMin; it is looser than the
+// final cutoff.  Candidates are appended to a per-lane buffer, not recombined:
+// recombining them on the spot makes a warp wait for one lane's table round trips,
+// and fills the table (and L2) with arrivals that the final cutoff rejects -- 3x more
+// slots claimed than tokens kept (profiles/r1_v5_ncu_summary.txt).
 //
 // Exact cutoff.  C* = min(new_weight) + adaptive_beam (faster-decoder.cc:240)
 // from the per-thread fp64 minima: the arc with the globally smallest
@@ -1026,22 +1019,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // (Loop state is kept in shared memory where it can be: the item loop below needs
   // every register it can get.)
   static_assert(TT <= kFrontCap, "front list smaller than a scan tile");
-#ifdef KD_NO_FRONT
-  for (int pass = 1; pass < 2; ++pass) {
-#else
   for (int pass = 0; pass < 2; ++pass) {
-#endif
     // pass 0 reads the front list the commit wrote, unless it overflowed (then it filters the block)
     const bool front_list =
         pass == 0 && static_cast<uint32_t>(ls.n_front) <= static_cast<uint32_t>(kFrontCap);
     const uint32_t un = static_cast<uint32_t>(front_list ? ls.n_front : ls.n_tok);
     for (uint32_t tile0 = 0; tile0 < un; tile0 += TT) {
     const double wcut = sh.wc;
-#ifdef KD_NO_FRONT
-    const double good = -inf;
-#else
     const double good = fmin(ls.good_cut, wcut);
-#endif
     const uint32_t tile_end = min(un, tile0 + TT);
     // chunk setup: 4 consecutive tokens per thread -> (cost, arc range or label
     // count) of the tokens to expand
