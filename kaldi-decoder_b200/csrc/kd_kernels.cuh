@@ -60,6 +60,9 @@ constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
 constexpr int kOrderBins = 512;           // buckets of the per-frame label order (1/16 wide)
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
+// 32-item windows a warp takes per scan step.  2 or 3 (more loads in flight per warp) make
+// the scan 5% faster and the other phases slower by as much (code size, registers).
+constexpr int kWin = 1;
 constexpr int kTileTokens = 2;            // tokens per thread in one scan tile
 constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
@@ -1148,28 +1151,32 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     }
     __syncthreads();
     // flat item loop: 32-item windows are dealt round-robin to the warps, so all warps
-    // start at the front of the flat space.  (One window per step: keeping several in
-    // flight made the loop body, and with it the kernel, too large for the instruction
-    // cache -- 100 -> 89 ms per launch going from 4 windows to 1.)
+    // start at the front of the flat space; kWin windows per step.
     {
       const uint32_t jw1 = n_flat;
 #pragma unroll 1
-      for (uint32_t jb = warp * 32; jb < jw1; jb += NW * 32) {
-        // compacted token owning item jb = largest t with t_ex[t] <= jb: 32-ary search,
-        // every lane probes one position per level (t_ex[0] = 0 <= jb always)
-        uint32_t t_lo = 0;
+      for (uint32_t jb0 = warp * 32; jb0 < jw1; jb0 += NW * 32 * kWin) {
+        int2 iw[kWin];      // {ilabel, weight bits} of the item's arc
+        uint32_t tt[kWin];  // compacted token of the item, kNoIdx if none
+        uint32_t aa[kWin];  // emitting arc index of the item
 #pragma unroll
-        for (uint32_t stride = kSearchTop; stride; stride >>= 5) {
-          const uint32_t pos = t_lo + lane * stride;
-          const bool le = pos < n_comp && t_ex[pos] <= jb;
-          t_lo += (__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u) * stride;
-        }
-        // item -> token: bit mask of the token boundaries (first item index of the 32
-        // tokens after t_lo) that fall inside the window
-        int2 iw = make_int2(1, 0);  // {ilabel, weight bits} of the item's arc
-        uint32_t tt = kNoIdx;       // compacted token of the item, kNoIdx if none
-        uint32_t aa = kNoIdx;       // emitting arc index of the item
-        {
+        for (int u = 0; u < kWin; ++u) {
+          const uint32_t jb = jb0 + u * (NW * 32);
+          iw[u] = make_int2(1, 0);
+          tt[u] = kNoIdx;
+          aa[u] = kNoIdx;
+          if (jb >= jw1) continue;  // warp-uniform
+          // compacted token owning item jb = largest t with t_ex[t] <= jb: 32-ary search,
+          // every lane probes one position per level (t_ex[0] = 0 <= jb always)
+          uint32_t t_lo = 0;
+#pragma unroll
+          for (uint32_t stride = kSearchTop; stride; stride >>= 5) {
+            const uint32_t pos = t_lo + lane * stride;
+            const bool le = pos < n_comp && t_ex[pos] <= jb;
+            t_lo += (__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u) * stride;
+          }
+          // item -> token: bit mask of the token boundaries (first item index of the 32
+          // tokens after t_lo) that fall inside the window
           const uint32_t j = jb + lane;
           const uint32_t bnd = t_ex[min(t_lo + 1 + lane, n_comp)];
           const uint32_t p = bnd - jb;  // >= 1: token t_lo owns item jb
@@ -1185,49 +1192,52 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               const int2 ent =
                   __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
               if (ent.y >= 0) {  // else: the state has no arc with this label
-                tt = t;
-                aa = (b & ~kLookupFlag) + static_cast<uint32_t>(ent.y);
-                iw = make_int2(static_cast<int>(lab), ent.x);
+                tt[u] = t;
+                aa[u] = (b & ~kLookupFlag) + static_cast<uint32_t>(ent.y);
+                iw[u] = make_int2(static_cast<int>(lab), ent.x);
               }
             } else {
-              tt = t;
-              aa = b + k;
-              iw = __ldg(P.e_iw + aa);
+              tt[u] = t;
+              aa[u] = b + k;
+              iw[u] = __ldg(P.e_iw + aa[u]);
             }
           }
         }
         const double cut_d = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
-        const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
-        const double tcst = t_cost[min(tt, static_cast<uint32_t>(TT - 1))];
-        const double nw = (widen(__int_as_float(iw.y)) + tcst) + ac;
-        // faster-decoder.cc:211 against the running cutoff
-        const bool is_cand = tt != kNoIdx && nw < cut_d;
-        // Candidates are appended warp-aggregated: about a third of the looked-up arcs
-        // pass the filter, and one shared-memory atomic per candidate on the single
-        // counter serialised the whole CTA.
-        const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
-        if (cmask == 0) continue;  // warp-uniform
-        uint32_t cbase = 0;
-        if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
-        cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
-        if (is_cand) {
-          const uint32_t tok_abs = base + t_tok[tt];
-          const unsigned long long nk = dkey(nw);
-          const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
-          if (e < P.ccap) {
-            __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
-                                          static_cast<uint32_t>(nk >> 32), aa, tok_abs));
-          } else if (SIMPLE) {
-            atomicOr(&sh.status, kStatusCandOverflow);
-          } else {
-            insert_arc(P, B, sh, aa, nk, tok_abs);  // buffer full: recombine now
-          }
-          if (nw < my_min) {
-            my_min = nw;
-            // faster-decoder.cc:215-217
-            const uint32_t fk = fkey(__double2float_ru(nw + ab));
-            if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
-              atomicMin(&sh.cut_fkey, fk);
+#pragma unroll
+        for (int u = 0; u < kWin; ++u) {
+          const double ac = widen(ROW_SMEM ? s_row[iw[u].x - 1] : -__ldg(row_g + iw[u].x - 1));
+          const double tcst = t_cost[min(tt[u], static_cast<uint32_t>(TT - 1))];
+          const double nw = (widen(__int_as_float(iw[u].y)) + tcst) + ac;
+          // faster-decoder.cc:211 against the running cutoff
+          const bool is_cand = tt[u] != kNoIdx && nw < cut_d;
+          // Candidates are appended warp-aggregated: about a third of the looked-up arcs
+          // pass the filter, and one shared-memory atomic per candidate on the single
+          // counter serialised the whole CTA.
+          const uint32_t cmask = __ballot_sync(0xFFFFFFFFu, is_cand);
+          if (cmask == 0) continue;  // warp-uniform
+          uint32_t cbase = 0;
+          if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
+          cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+          if (is_cand) {
+            const uint32_t tok_abs = base + t_tok[tt[u]];
+            const unsigned long long nk = dkey(nw);
+            const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
+            if (e < P.ccap) {
+              __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
+                                            static_cast<uint32_t>(nk >> 32), aa[u], tok_abs));
+            } else if (SIMPLE) {
+              atomicOr(&sh.status, kStatusCandOverflow);
+            } else {
+              insert_arc(P, B, sh, aa[u], nk, tok_abs);  // buffer full: recombine now
+            }
+            if (nw < my_min) {
+              my_min = nw;
+              // faster-decoder.cc:215-217
+              const uint32_t fk = fkey(__double2float_ru(nw + ab));
+              if (fk < *reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey))
+                atomicMin(&sh.cut_fkey, fk);
+            }
           }
         }
       }
