@@ -168,9 +168,9 @@ def make_device_logprobs(g, n_utts, T, seed, peak, device):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of kd_advance_kernel from the committed
-# `ncu --set full` capture (profiles/r1_e2_ncu_summary.txt: 9.77 + 6.78 GB for a launch of
+# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt: 9.58 + 6.72 GB for a launch of
 # 1024 lanes x 100 frames of this workload), per lane-frame.  Only valid for config C3.
-NCU_DRAM_BYTES_PER_LANE_FRAME_C3 = (9.404027e9 + 7.171809e9) / (1024 * 100)
+NCU_DRAM_BYTES_PER_LANE_FRAME_C3 = (9.580444e9 + 6.723989e9) / (1024 * 100)
 
 
 def algorithmic_bytes(st: dict, cols: int) -> float:
@@ -366,7 +366,7 @@ def main():
                          "traffic": (NCU_DRAM_BYTES_PER_LANE_FRAME_C3 * lanes * T
                                      if args.config == "C3" and args.peak == 12.0 else None),
                          "traffic_note": "DRAM bytes per launch scaled from the ncu capture in "
-                                         "profiles/r1_e2_ncu_summary.txt (per lane-frame x lanes x frames)",
+                                         "profiles/r1_final_ncu_summary.txt (per lane-frame x lanes x frames)",
                          "kernel": "kd_advance_kernel", "kernel_ms": k_ms,
                          "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                          "counters": st},
