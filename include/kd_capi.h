@@ -190,7 +190,8 @@ KD_API int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs
 
 /* The live tokens of a lane (state, cost), in device order (unordered): the
  * contents of the reference's `toks_` list.  *n is the token count even if it
- * exceeds cap. */
+ * exceeds cap (then nothing is written).  KD_SEARCH_SIMPLE: what is written is
+ * SimpleDecoder's cur_toks_ after PruneToks, and *n is then the number written. */
 KD_API int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *states,
                                   double *costs, int64_t *n);
 

@@ -111,6 +111,7 @@ struct kd_decoder {
 
   std::vector<int32_t> frames;  // host mirror of num_frames_decoded_, -1 = not initialised
   std::vector<int32_t> status;
+  std::vector<uint8_t> bp_valid;  // best_path_prepare ran for the lane's current tokens
   int last_use_final = 1;
 
   cudaStream_t streams[kNumStreams] = {};
@@ -612,6 +613,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   KD_CUDA(cudaEventCreate(&d->ev_end));
   d->frames.assign(L, -1);
   d->status.assign(L, 0);
+  d->bp_valid.assign(L, 0);
   KD_CUDA(cudaDeviceSynchronize());
   *out = d;
   return KD_OK;
@@ -691,6 +693,7 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
   for (int32_t i = 0; i < n; ++i) {
     const int32_t lane = lanes[i];
     d->frames[lane] = 0;
+    d->bp_valid[lane] = 0;
     d->status[lane] = d->h_lanes[lane].status;
     if (d->status[lane] != 0)
       return Fail(KD_ERR_OVERFLOW, std::string("InitDecoding: ") + StatusText(d->status[lane]));
@@ -881,6 +884,7 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
   for (int32_t i = 0; i < m; ++i) {
     const int32_t lane = work[i].lane;
     d->frames[lane] = d->h_lanes[lane].frames_decoded;
+    d->bp_valid[lane] = 0;  // the path parked in the candidate buffer is gone
     d->status[lane] = d->h_lanes[lane].status;
     if (d->status[lane] != 0 && bad == 0) bad = d->status[lane];
   }
@@ -921,6 +925,7 @@ int kd_decoder_best_path_prepare(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (rc) return rc;
   d->last_use_final = use_final_probs ? 1 : 0;
   for (int32_t i = 0; i < n; ++i) {
+    d->bp_valid[lanes[i]] = 1;
     const kd::LaneState &L = d->h_lanes[lanes[i]];
     if (ok) ok[i] = L.bp_ok;
     if (reached_final) reached_final[i] = L.bp_final;
@@ -944,6 +949,10 @@ int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (!out_offsets || total_arcs < 0) return Fail(KD_ERR_INVALID, "bad output layout");
   KD_CUDA(cudaSetDevice(d->device));
   for (int32_t i = 0; i < n; ++i) {
+    if (!d->bp_valid[lanes[i]])
+      return Fail(KD_ERR_INVALID,
+                  "kd_decoder_best_path_prepare must run after the last InitDecoding / "
+                  "AdvanceDecoding of the lane");
     const kd::LaneState &L = d->h_lanes[lanes[i]];
     if (L.bp_ok && (out_offsets[i] < 0 || out_offsets[i] + L.bp_len > total_arcs))
       return Fail(KD_ERR_INVALID, "best path does not fit the output arrays");
@@ -980,8 +989,7 @@ int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
   int32_t *d_il = d->d_path, *d_ol = d->d_path + nb;
   float *d_gw = reinterpret_cast<float *>(d->d_path + 2 * nb);
   float *d_aw = reinterpret_cast<float *>(d->d_path + 3 * nb);
-  const int tb = 32;
-  kd::kd_best_fill_kernel<<<(n + tb - 1) / tb, tb, 0, s>>>(P, d->d_out_off, d_il, d_ol, d_gw, d_aw);
+  kd::kd_best_fill_kernel<<<n, 128, 0, s>>>(P, d->d_out_off, d_il, d_ol, d_gw, d_aw);
   KD_CUDA(cudaGetLastError());
   KD_CUDA(cudaMemcpyAsync(d->h_path, d->d_path, 4 * nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   KD_CUDA(cudaStreamSynchronize(s));
@@ -1073,13 +1081,18 @@ int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *st
                      cudaMemcpyDeviceToHost));
   KD_CUDA(cudaMemcpy(co.data(), d->a_cost + base, sizeof(double) * L.n_tok,
                      cudaMemcpyDeviceToHost));
+  // SimpleDecoder search: PruneToks (simple-decoder.cc:251-279) is applied to the view
+  const bool pruned_view = d->simple && L.frames_decoded > 0;
+  const double limit = L.best_cost + static_cast<double>(d->opts.beam);
   int64_t k = 0;
   for (int32_t i = 0; i < L.n_tok && k < L.n_live; ++i) {
     if (st[i] < 0) continue;
+    if (pruned_view && !(co[i] < limit)) continue;
     if (states) states[k] = st[i];
     if (costs) costs[k] = co[i];
     ++k;
   }
+  if (n) *n = k;
   return KD_OK;
 }
 

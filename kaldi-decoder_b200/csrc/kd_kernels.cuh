@@ -112,6 +112,8 @@ struct __align__(16) LaneState {
   long long bp_len;
   float bp_final_w;
   double bp_value;         // selection cost of the best token (cost, or cost + final weight)
+  int32_t bp_stored;       // the path's token indices are in the lane's candidate buffer
+  int32_t pad1;
 };
 
 struct AdvanceItem {
@@ -911,6 +913,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   double wc;
   float abf;
   lane_cutoff<THREADS>(P, cost, n, ls, sh, &wc, &abf);
+  // SimpleDecoder does not prune after InitDecoding: its first frame expands every token
+  if (SIMPLE && ls.frames_decoded == 0) wc = inf;
   const double ab = static_cast<double>(abf);
   if (tid == 0) sh.wc = wc;
   __syncthreads();
@@ -1521,16 +1525,23 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
       L->bp_value = inf;
     } else {
       L->bp_value = rv;
+      // The only walk of the backpointer chain: the token indices met on the way are
+      // parked in the lane's candidate buffer (idle between AdvanceDecoding calls), so
+      // the arcs can then be written out by all threads at once.
+      uint32_t *path = reinterpret_cast<uint32_t *>(B.cand);
+      const long long path_cap = 4ll * P.ccap;
       long long len = 0;
       uint32_t t = s_best_tok;
       while (true) {
         unsigned long long link = B.a_link[t];
         uint32_t arc = static_cast<uint32_t>(link >> 32);
         if (arc == kNoArc) break;
+        if (len < path_cap) path[len] = t;
         ++len;
         t = static_cast<uint32_t>(link);
       }
       L->bp_ok = 1;
+      L->bp_stored = len <= path_cap ? 1 : 0;
       L->bp_len = len;
       L->bp_best_tok = s_best_tok;
       L->bp_best_state = rs;
@@ -1542,15 +1553,55 @@ __global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
 // Writes the best path of lane items[b].lane in time order at out_off[b]
 // (faster-decoder.cc:393-402: graph = arc weight, acoustic = float(cost -
 // prev cost) - graph).
+__device__ __forceinline__ void write_path_arc(const Params &P, uint32_t arc, double c, double pc,
+                                               long long pos, int32_t *il, int32_t *ol, float *gw,
+                                               float *aw) {
+  int32_t ilab, olab;
+  float graph;
+  if (arc & kEpsFlag) {
+    const int4 a = __ldg(P.n_arc + (arc & ~kEpsFlag));
+    ilab = 0;
+    olab = a.x;
+    graph = __int_as_float(a.y);
+  } else {
+    const int2 iw = __ldg(P.e_iw + arc);
+    const int2 no = __ldg(P.e_no + arc);
+    ilab = iw.x;
+    olab = no.y;
+    graph = __int_as_float(iw.y);
+  }
+  const float tot = static_cast<float>(c - pc);
+  il[pos] = ilab;
+  ol[pos] = olab;
+  gw[pos] = graph;
+  aw[pos] = tot - graph;
+}
+
+// One CTA per lane.  With the token indices of the path at hand (kd_best_select_kernel)
+// every arc is independent; otherwise (path longer than the buffer) thread 0 walks the chain.
 __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t *il, int32_t *ol,
                                     float *gw, float *aw) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x;
   if (b >= P.n_items) return;
   const int lane = P.items[b].lane;
   const LaneBuf B = lane_buffers(P, lane);
   const LaneState *L = P.lanes + lane;
   if (!L->bp_ok) return;
-  long long pos = out_off[b] + L->bp_len - 1;
+  const long long len = L->bp_len;
+  const long long last = out_off[b] + len - 1;
+  if (L->bp_stored) {
+    const uint32_t *path = reinterpret_cast<const uint32_t *>(B.cand);
+    for (long long i = threadIdx.x; i < len; i += blockDim.x) {
+      const uint32_t t = path[i];
+      const unsigned long long link = B.a_link[t];
+      const uint32_t prev = static_cast<uint32_t>(link);
+      write_path_arc(P, static_cast<uint32_t>(link >> 32), B.a_cost[t], B.a_cost[prev], last - i,
+                     il, ol, gw, aw);
+    }
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  long long pos = last;
   uint32_t t = L->bp_best_tok;
   double c = B.a_cost[t];
   unsigned long long link = B.a_link[t];
@@ -1562,25 +1613,7 @@ __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t 
     // loads that only feed this step's output
     const unsigned long long link_next = B.a_link[prev];
     double pc = B.a_cost[prev];
-    int32_t ilab, olab;
-    float graph;
-    if (arc & kEpsFlag) {
-      const int4 a = __ldg(P.n_arc + (arc & ~kEpsFlag));
-      ilab = 0;
-      olab = a.x;
-      graph = __int_as_float(a.y);
-    } else {
-      const int2 iw = __ldg(P.e_iw + arc);
-      const int2 no = __ldg(P.e_no + arc);
-      ilab = iw.x;
-      olab = no.y;
-      graph = __int_as_float(iw.y);
-    }
-    float tot = static_cast<float>(c - pc);
-    il[pos] = ilab;
-    ol[pos] = olab;
-    gw[pos] = graph;
-    aw[pos] = tot - graph;
+    write_path_arc(P, arc, c, pc, pos, il, ol, gw, aw);
     --pos;
     t = prev;
     c = pc;

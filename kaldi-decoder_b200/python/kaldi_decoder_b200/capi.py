@@ -307,7 +307,8 @@ class LaneDecoder:
         if n.value:
             _check(lib().kd_decoder_dump_tokens(self.h, int(lane), n.value, st.ctypes.data,
                                                 co.ctypes.data, C.byref(n)))
-        return st, co
+        # (SimpleDecoder search: the second call returns the PruneToks view, possibly shorter)
+        return st[:n.value], co[:n.value]
 
     def final_relative_cost(self, lane: int = 0) -> float:
         v = C.c_float(0)

@@ -22,6 +22,17 @@
 //          whenever the reference admits no "extra" tokens that later matter
 //          and no exact cost tie decides a backpointer.
 //
+//   mode 2 "simple": the order-independent statement of the reference's SimpleDecoder
+//          (simple-decoder.cc:29-41, 150-279; simple-decoder.h:89-101): beam-only
+//          pruning; an emitting arc is admitted when (cost + w) + ac < C*, C* =
+//          min of that + beam (simple-decoder.cc:168-176), but the token stores
+//          cost + float(w + ac) (simple-decoder.h:96); the closure runs under
+//          best stored cost + beam with `>` (simple-decoder.cc:196-215) and expands
+//          every token; PruneToks (cc:251-279, `cost < best + beam`) is applied to
+//          what the accessors return and to what the next frame expands.  Pinned
+//          against the unmodified simple-decoder.cc in oracle/_ref
+//          (tests/test_oracle_vs_reference.py).
+//
 // Both modes carry counters (tokens, arcs, extras, ties, binding frames) used
 // for the algorithmic-bytes figure and the parity report.
 //
@@ -179,7 +190,8 @@ class Decoder {
     if (g_->start < 0) throw std::runtime_error("graph has no start state");
     int32_t t = NewTok(-1, -1, 0.0);
     map_.Insert(g_->start, t);
-    Closure(static_cast<double>(std::numeric_limits<float>::max()));
+    // simple-decoder.cc:29-41: ProcessNonemitting's own cutoff, best (0) + beam
+    Closure(mode_ == 2 ? 0.0 + o_.beam : static_cast<double>(std::numeric_limits<float>::max()));
     frames_ = 0;
     stats_ = Stats();
   }
@@ -194,7 +206,8 @@ class Decoder {
     if (max_frames >= 0) target = std::min(target, frames_ + max_frames);
     while (frames_ < target) {
       const float *row = p + static_cast<int64_t>(frames_ - offset) * cols;
-      double c = (mode_ == 0) ? EmitReferenceOrder(row) : EmitCanonical(row);
+      double c = mode_ == 0 ? EmitReferenceOrder(row)
+                            : (mode_ == 1 ? EmitCanonical(row) : EmitSimple(row));
       Closure(c);
       stats_.frames++;
       int64_t n = static_cast<int64_t>(map_.Count());
@@ -210,6 +223,7 @@ class Decoder {
   bool ReachedFinal() const {
     std::vector<int32_t> order;
     map_.ListOrder(&order);
+    DropPruned(&order);
     for (int32_t c : order) {
       const auto &cell = map_.At(c);
       if (toks_[cell.tok].cost != kInf && g_->fin[cell.state] != kInfF()) return true;
@@ -329,9 +343,23 @@ class Decoder {
 
   static float kInfF() { return std::numeric_limits<float>::infinity(); }
 
+  // mode 2: the cells PruneToks keeps (simple-decoder.cc:251-279); not applied before the
+  // first frame (InitDecoding does not prune)
+  void DropPruned(std::vector<int32_t> *order) const {
+    if (mode_ != 2 || frames_ <= 0) return;
+    double best = kInf;
+    for (int32_t c : *order) best = std::min(best, toks_[map_.At(c).tok].cost);
+    const double cutoff = best + o_.beam;
+    size_t k = 0;
+    for (int32_t c : *order)
+      if (toks_[map_.At(c).tok].cost < cutoff) (*order)[k++] = c;
+    order->resize(k);
+  }
+
   void IterOrder(std::vector<int32_t> *order) const {
     map_.ListOrder(order);
-    if (mode_ == 1) {
+    DropPruned(order);
+    if (mode_ != 0) {
       std::sort(order->begin(), order->end(), [this](int32_t a, int32_t b) {
         return map_.At(a).state < map_.At(b).state;
       });
@@ -558,13 +586,76 @@ class Decoder {
     return cstar;
   }
 
+  // SimpleDecoder::ProcessEmitting (simple-decoder.cc:150-192), order-independent
+  // statement.  Returns ProcessNonemitting's cutoff (cc:196-204).
+  double EmitSimple(const float *row) {
+    std::vector<OrderedStateMap::Cell> old;
+    map_.Take(&old);
+    stats_.tokens_in += static_cast<int64_t>(old.size());
+    MaybeGrow(old.size());
+    // PruneToks of the previous frame (cc:251-279); none before the first frame
+    double best = kInf;
+    for (const auto &cell : old) best = std::min(best, toks_[cell.tok].cost);
+    const double keep_below = frames_ > 0 ? best + o_.beam : kInf;
+    auto kept = [&](double c) { return frames_ > 0 ? c < keep_below : true; };
+    double min_pv = kInf;
+    for (const auto &cell : old) {
+      double c = toks_[cell.tok].cost;
+      if (!kept(c)) continue;
+      int32_t s = cell.state;
+      for (int64_t a = g_->off[s]; a < g_->off[s + 1]; ++a) {
+        if (g_->il[a] == 0) continue;
+        double pv = c + static_cast<double>(g_->w[a]) + static_cast<double>(-row[g_->il[a] - 1]);
+        if (pv < min_pv) min_pv = pv;
+      }
+    }
+    const double cstar = min_pv + o_.beam;  // final value of the running cutoff (cc:171-176)
+    double min_stored = kInf;
+    for (const auto &cell : old) {
+      int32_t t = cell.tok;
+      double c = toks_[t].cost;
+      if (kept(c)) {
+        stats_.tokens_expanded++;
+        int32_t s = cell.state;
+        for (int64_t a = g_->off[s]; a < g_->off[s + 1]; ++a) {
+          if (g_->il[a] == 0) continue;
+          stats_.emit_arcs++;
+          const float ac = -row[g_->il[a] - 1];
+          double pv = c + static_cast<double>(g_->w[a]) + static_cast<double>(ac);
+          if (!(pv < cstar)) continue;  // cc:170
+          stats_.admitted++;
+          const float wa = g_->w[a] + ac;  // float sum, simple-decoder.h:96
+          const double stored = c + static_cast<double>(wa);
+          if (stored < min_stored) min_stored = stored;
+          int32_t nt = NewTok(static_cast<int32_t>(a), t, stored);
+          int32_t cidx = map_.Insert(g_->ns[a], nt);
+          auto &dst = map_.At(cidx);
+          if (dst.tok != nt) {
+            const Tok &cur = toks_[dst.tok];
+            bool better = stored < cur.cost || (stored == cur.cost && a < cur.arc);
+            if (stored == cur.cost) stats_.emit_ties++;
+            if (better) {
+              Release(dst.tok);
+              dst.tok = nt;
+            } else {
+              Release(nt);
+            }
+          }
+        }
+      }
+      Release(t);
+    }
+    frames_++;
+    return min_stored + o_.beam;
+  }
+
   // faster-decoder.cc:59-119.  Mode 0 keeps the LIFO worklist; mode 1 sweeps
   // to the same fixed point (costs are order-independent; on an exact tie the
   // incumbent stays in both).
   void Closure(double cutoff) {
     std::vector<int32_t> work;
     map_.ListOrder(&work);
-    if (mode_ == 1) {
+    if (mode_ != 0) {
       // deterministic: by state id; processed front to back in sweeps
       std::sort(work.begin(), work.end(), [this](int32_t a, int32_t b) {
         return map_.At(a).state < map_.At(b).state;
@@ -588,7 +679,8 @@ class Decoder {
     int32_t s = map_.At(c).state;
     int32_t t = map_.At(c).tok;
     double cost = toks_[t].cost;
-    if (cost > cutoff) return;
+    // (SimpleDecoder expands every token, simple-decoder.cc:206-211)
+    if (mode_ != 2 && cost > cutoff) return;
     stats_.all_arcs_scanned += g_->off[s + 1] - g_->off[s];
     for (int64_t a = g_->off[s]; a < g_->off[s + 1]; ++a) {
       if (g_->il[a] != 0) continue;

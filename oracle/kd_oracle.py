@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libkd_oracle.so")
 
 REFERENCE_ORDER = 0
 CANONICAL = 1
+SIMPLE = 2  # order-independent SimpleDecoder (beam from Options.beam; other options unused)
 
 STAT_NAMES = ("frames", "tokens_in", "tokens_expanded", "emit_arcs", "eps_arcs", "admitted",
               "extras", "emit_ties", "eps_ties", "tokens_out", "max_tokens", "binding_max",

@@ -158,6 +158,17 @@ def test_error_behaviour_matches_reference_assertions():
         dec.advance([0], [np.zeros((12, 10), np.float32)])
     with pytest.raises(capi.KdError, match="lane id"):
         dec.init([2])
+    # step 2 of GetBestPath without step 1 since the last advance
+    dec.best_paths([0])
+    dec.advance([0], [np.vstack([lp, lp[:3]])])
+    la = np.zeros(1, np.int32)
+    off = np.zeros(1, np.int64)
+    buf = np.zeros(64, np.int32)
+    with pytest.raises(capi.KdError, match="best_path_prepare"):
+        capi._check(capi.lib().kd_decoder_best_path_fetch(
+            dec.h, 1, la.ctypes.data, off.ctypes.data, 64, buf.ctypes.data, buf.ctypes.data,
+            buf.ctypes.data, buf.ctypes.data, None))
+    assert len(dec.best_paths([0])[0].ilabels) == 13
     # a graph without start state (faster-decoder.cc:47)
     with pytest.raises(capi.KdError, match="kNoStateId"):
         capi.DeviceGraph(g.num_states, -1, g.row_off, g.ilabel, g.olabel, g.weight, g.nextstate,

@@ -5,9 +5,9 @@ import math
 import numpy as np
 import pytest
 
-from common import rel_close, small_graph
+from common import rel_close, small_graph, sorted_tokens
 from kaldi_decoder_b200 import capi, synth
-from oracle import kd_ref
+from oracle import kd_oracle, kd_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -107,3 +107,35 @@ def test_python_simple_decoder_drop_in():
     assert dec.num_frames_decoded() == 80
     ok3, lat3 = dec.get_best_path()
     assert ok3 and list(kd.get_linear_symbol_sequence(lat3)[1]) == list(isyms)
+
+
+@pytest.mark.parametrize("gname,beam,peak", [("H", 6.0, 4), ("HL", 8.0, 6), ("HLG", 10.0, 5),
+                                             ("HLG", 3.0, 8)])
+def test_simple_search_token_sets_equal_the_oracle_every_frame(gname, beam, peak):
+    """Device token list (PruneToks view) == oracle mode 2 after every frame: same states,
+    bit-identical fp64 costs; raw best paths arc for arc."""
+    g = small_graph(gname)
+    mat = synth.make_logprobs(g, 60, seed=11 + int(beam), peak=peak)
+    dg = capi.DeviceGraph.from_graph(g)
+    dec = capi.LaneDecoder(dg, capi.make_options(beam=beam), max_lanes=1,
+                           search=capi.KD_SEARCH_SIMPLE, hash_capacity=1 << 16,
+                           arena_records=1 << 19)
+    orc = kd_oracle.OracleDecoder(kd_oracle.OracleGraph(g), kd_ref.Options(beam=beam),
+                                  kd_oracle.SIMPLE)
+    dec.init([0])
+    orc.init_decoding()
+    for f in range(mat.shape[0] + 1):
+        gs, gc = sorted_tokens(*dec.tokens(0))
+        os_, oc = sorted_tokens(*orc.tokens())
+        assert np.array_equal(gs, os_), (f, len(gs), len(os_))
+        assert np.array_equal(gc, oc), f
+        if f < mat.shape[0]:
+            dec.advance([0], [mat], max_num_frames=1)
+            orc.advance_decoding(mat, 0, 1)
+    p = dec.best_paths([0], True)[0]
+    o = orc.get_best_path(True, raw=True)
+    assert p.ok == o.ok
+    if o.ok:
+        assert rel_close(p.total_cost, o.total_cost, 1e-6)
+        if np.array_equal(p.ilabels, o.ilabels):
+            assert np.array_equal(p.graph, o.graph) and np.array_equal(p.acoustic, o.acoustic)

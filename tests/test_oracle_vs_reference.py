@@ -3,7 +3,7 @@ object code).  Skipped where the compiled reference is not available."""
 import numpy as np
 import pytest
 
-from common import OPTION_SETS, same_labels, small_graph
+from common import OPTION_SETS, rel_close, same_labels, small_graph
 from kaldi_decoder_b200 import synth
 from oracle import kd_oracle, kd_ref
 
@@ -100,3 +100,43 @@ def test_random_fsts_negative_weights_nondeterminism(seed):
     a, b = r.get_best_path(), o.get_best_path()
     assert a.ok == b.ok and np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.graph, b.graph)
     assert np.array_equal(a.acoustic, b.acoustic) and np.array_equal(a.final, b.final)
+
+
+def _frc(states, costs, final):
+    """SimpleDecoder::FinalRelativeCost (simple-decoder.cc:78-101) from a token list."""
+    if len(states) == 0:
+        return float("inf")
+    f = final[states].astype(np.float64)
+    with np.errstate(invalid="ignore"):
+        return float(np.float32((costs + f).min() - costs.min()))
+
+
+@pytest.mark.parametrize("gname,beam,peak", [("H", 6.0, 4), ("HL", 8.0, 6), ("HLG", 10.0, 5),
+                                             ("HLG", 3.0, 8), ("HL", 14.0, 3)])
+def test_simple_mode_matches_reference_simple_decoder(gname, beam, peak):
+    """oracle mode 2 (order-independent SimpleDecoder) vs the unmodified simple-decoder.cc,
+    after every frame: ReachedFinal, FinalRelativeCost, best path."""
+    import math
+    g = small_graph(gname)
+    mat = synth.make_logprobs(g, 50, seed=77 + int(beam), peak=peak)
+    orc = kd_oracle.OracleDecoder(kd_oracle.OracleGraph(g), kd_ref.Options(beam=beam),
+                                  kd_oracle.SIMPLE)
+    ref = kd_ref.RefSimpleDecoder(kd_ref.RefGraph(g), beam)
+    orc.init_decoding()
+    ref.init_decoding()
+    fin = np.asarray(g.final)
+    for f in range(mat.shape[0] + 1):
+        assert orc.reached_final() == ref.reached_final(), f
+        st, co = orc.tokens()
+        a, b = _frc(st, co, fin), ref.final_relative_cost()
+        assert (math.isinf(a) and math.isinf(b)) or abs(a - b) <= 1e-4 * max(1.0, abs(b)), (f, a, b)
+        for ufp in (True, False):
+            p, r = orc.get_best_path(ufp), ref.get_best_path(ufp)
+            assert p.ok == r.ok
+            if r.ok:
+                assert rel_close(p.total_cost, r.total_cost, 1e-5), (f, ufp)
+                if not (np.array_equal(p.isyms, r.isyms) and np.array_equal(p.osyms, r.osyms)):
+                    assert p.total_cost == pytest.approx(r.total_cost, rel=1e-6)
+        if f < mat.shape[0]:
+            orc.advance_decoding(mat, 0, 1)
+            ref.advance_decoding(mat, 0, 1)
