@@ -810,7 +810,17 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       d->h_items[i].logp = d->d_stage + pos;
       pos += static_cast<size_t>(work[i].n_rows) * cols;
     }
-    const int32_t n_chunks = (max_rows + F - 1) / F;
+    // Chunk ends: the first chunks are small (F/16, F/8, ... frames) so the lanes start
+    // after a fraction of a millisecond instead of one full chunk's copy time; the copy
+    // engine delivers frames about twice as fast as the lanes consume them, so it stays
+    // ahead once it is.
+    std::vector<int32_t> ends;
+    for (int32_t r = 0, step = std::max(4, F / 16); r < max_rows;) {
+      r = std::min(max_rows, r + step);
+      ends.push_back(r);
+      step = std::min(F, step * 2);
+    }
+    const int32_t n_chunks = static_cast<int32_t>(ends.size());
     if (n_chunks > d->progress_cap) {
       KD_CUDA(cudaDeviceSynchronize());
       if (d->h_progress) cudaFreeHost(d->h_progress);
@@ -846,9 +856,10 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
     if (rc) return rc;
     KD_CUDA(cudaEventRecord(d->ev_end, sc));
     for (int32_t c = 0; c < n_chunks; ++c) {
-      const int32_t r0 = c * F;
+      const int32_t r0 = c == 0 ? 0 : ends[c - 1];
+      const int32_t Fc = ends[c] - r0;  // frames of this chunk
       if (uniform) {
-        const int32_t rows_c = std::min(F, work[0].n_rows - r0);
+        const int32_t rows_c = std::min(Fc, work[0].n_rows - r0);
         const size_t lane_floats = static_cast<size_t>(work[0].n_rows) * cols;
         KD_CUDA(cudaMemcpy2DAsync(d->d_stage + static_cast<size_t>(r0) * cols,
                                   lane_floats * sizeof(float),
@@ -859,14 +870,14 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       } else {
         for (int32_t i = 0; i < m; ++i) {
           if (r0 >= work[i].n_rows) continue;
-          const int32_t rows_c = std::min(F, work[i].n_rows - r0);
+          const int32_t rows_c = std::min(Fc, work[i].n_rows - r0);
           KD_CUDA(cudaMemcpyAsync(
               const_cast<float *>(d->h_items[i].logp) + static_cast<size_t>(r0) * cols,
               work[i].src + static_cast<size_t>(r0) * cols,
               sizeof(float) * static_cast<size_t>(rows_c) * cols, cudaMemcpyHostToDevice, sx));
         }
       }
-      d->h_progress[c] = std::min(max_rows, r0 + F);
+      d->h_progress[c] = ends[c];
       KD_CUDA(cudaMemcpyAsync(d->d_progress, d->h_progress + c, sizeof(int32_t),
                               cudaMemcpyHostToDevice, sx));
     }
