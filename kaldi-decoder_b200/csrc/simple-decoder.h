@@ -35,18 +35,18 @@ class SimpleDecoder {
   SimpleDecoder &operator=(const SimpleDecoder &) = delete;
   ~SimpleDecoder();
 
-  /// Decode this utterance.  Returns true if any tokens reached the end of the
-  /// file (regardless of whether they are in a final state).
+  // InitDecoding + AdvanceDecoding over every ready frame; true iff some token is alive
+  // afterwards, final state or not.
   bool Decode(DecodableInterface *decodable);
 
   bool ReachedFinal() const;
 
-  // GetBestPath gets the decoding traceback; false (and an empty FST) if no token
-  // survived.  With use_final_probs and a final state active, final-probs are included.
+  // Linear lattice of the cheapest live token's history; false (and an empty FST) when no
+  // token is alive.  Final weights take part only if use_final_probs and ReachedFinal().
   bool GetBestPath(fst::Lattice *fst_out, bool use_final_probs = true) const;
 
-  /// Difference between the best cost including final-probs and the best cost
-  /// without them on the last frame; infinity if no final state was active.
+  // min(cost + final weight) - min(cost) over the live tokens; +inf without an active
+  // final state.
   float FinalRelativeCost() const;
 
   void InitDecoding();
