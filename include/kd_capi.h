@@ -65,7 +65,8 @@ typedef struct kd_decoder_config {
                                tokens alive in one frame must stay <= capacity / 2     */
   int64_t arena_records;    /* per-lane backpointer-store records (sum over frames of
                                tokens alive at frame end), 20 bytes each               */
-  int32_t threads_per_lane; /* 128/160/192/256/512; default chosen per launch         */
+  int32_t threads_per_lane; /* 128/160/192/224/256/384/512; default: the widest
+                               that keeps all lanes of a call resident at once         */
   int32_t chunk_frames;     /* host-memory advance: frames per copy/search pipeline
                                stage (default 128)                                     */
   int32_t search;           /* KD_SEARCH_FASTER (default) or KD_SEARCH_SIMPLE          */

@@ -177,11 +177,14 @@ kd::Params MakeParams(const kd_decoder *d) {
   return P;
 }
 
+// The widest lane that still lets every lane of the call be resident at once (one wave):
+// 512 threads x 1 lane per SM, 384 x 2, 256 x 3, 160 x 7.
 int PickThreads(const kd_decoder *d, int n_items) {
   if (d->threads > 0) return d->threads;
-  if (n_items >= 4 * d->num_sms) return 160;
-  if (n_items >= 2 * d->num_sms) return 256;
-  return 512;
+  if (n_items <= d->num_sms) return 512;
+  if (n_items <= 2 * d->num_sms) return 384;
+  if (n_items <= 3 * d->num_sms) return 256;
+  return 160;
 }
 
 template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM>
@@ -248,10 +251,12 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
       return LaunchAdvanceT<224, 7>(d, P, n_items, s);
     case 256:
       return LaunchAdvanceT<256, 3>(d, P, n_items, s);
+    case 384:
+      return LaunchAdvanceT<384, 2>(d, P, n_items, s);
     case 512:
       return LaunchAdvanceT<512, 1>(d, P, n_items, s);
     default:
-      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 160, 192, 256 or 512");
+      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 160, 192, 224, 256, 384 or 512");
   }
 }
 
@@ -532,9 +537,9 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->qcap = p2;
   d->ccap = p2 / 4;
   if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 && c.threads_per_lane != 192 && c.threads_per_lane != 224 &&
-      c.threads_per_lane != 256 && c.threads_per_lane != 512) {
+      c.threads_per_lane != 256 && c.threads_per_lane != 384 && c.threads_per_lane != 512) {
     delete d;
-    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 256 or 512");
+    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 224, 256, 384 or 512");
   }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
   if (c.search != KD_SEARCH_FASTER && c.search != KD_SEARCH_SIMPLE) {
