@@ -178,12 +178,13 @@ kd::Params MakeParams(const kd_decoder *d) {
 }
 
 // The widest lane that still lets every lane of the call be resident at once (one wave):
-// 512 threads x 1 lane per SM, 384 x 2, 256 x 3, 160 x 7.
+// 512 threads x 1 lane per SM, 384 x 2, 256 x 4, 192 x 5, 160 x 7.
 int PickThreads(const kd_decoder *d, int n_items) {
   if (d->threads > 0) return d->threads;
   if (n_items <= d->num_sms) return 512;
   if (n_items <= 2 * d->num_sms) return 384;
-  if (n_items <= 3 * d->num_sms) return 256;
+  if (n_items <= 4 * d->num_sms) return 256;
+  if (n_items <= 5 * d->num_sms) return 192;
   return 160;
 }
 
@@ -246,11 +247,11 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
     case 160:
       return LaunchAdvanceT<160, 7>(d, P, n_items, s);
     case 192:
-      return LaunchAdvanceT<192, 7>(d, P, n_items, s);
+      return LaunchAdvanceT<192, 5>(d, P, n_items, s);
     case 224:
       return LaunchAdvanceT<224, 7>(d, P, n_items, s);
     case 256:
-      return LaunchAdvanceT<256, 3>(d, P, n_items, s);
+      return LaunchAdvanceT<256, 4>(d, P, n_items, s);
     case 384:
       return LaunchAdvanceT<384, 2>(d, P, n_items, s);
     case 512:
