@@ -310,3 +310,29 @@ def test_full_size_properties_on_the_bench_graph():
         emit = a.ilabels != 0
         lp = mats[u][np.arange(T), a.ilabels[emit] - 1].astype(np.float64)
         assert abs(a.acoustic.astype(np.float64).sum() + lp.sum()) < 1e-2
+
+
+def test_path_batch_views_and_copies():
+    """best_paths(copy=False) returns views of the decoder's pinned buffer (valid until the
+    next call); copy=True owns its arrays; PathBatch behaves like a sequence."""
+    g = small_graph("HLG")
+    opts = dict(beam=12.0, max_active=300, min_active=20)
+    dec = _decoder(g, opts, 3)
+    mats = [synth.make_logprobs(g, 40 + 10 * u, seed=60 + u, peak=7) for u in range(3)]
+    dec.init([0, 1, 2])
+    dec.advance([0, 1, 2], mats)
+    owned = dec.best_paths([0, 1, 2])
+    views = dec.best_paths([0, 1, 2], copy=False)
+    assert len(owned) == len(views) == 3
+    for a, b in zip(owned, views):
+        assert a.ok and b.ok
+        assert np.array_equal(a.ilabels, b.ilabels) and np.array_equal(a.graph, b.graph)
+    assert [len(p.ilabels) for p in owned[1:]] == [len(owned[1].ilabels), len(owned[2].ilabels)]
+    assert np.array_equal(owned[-1].olabels, owned[2].olabels)
+    with pytest.raises(IndexError):
+        owned[3]
+    keep = [p.ilabels.copy() for p in views]
+    # another call reuses the pinned buffer: the owned copy is unaffected
+    dec.best_paths([2])
+    for a, k in zip(owned, keep):
+        assert np.array_equal(a.ilabels, k)
