@@ -74,3 +74,33 @@ def _iter_kaldifst(kaldifst, fst, s):
     while not it.done():
         yield it.value
         it.next()
+
+
+def advance_decoding_cuda(decoder: "BatchFasterDecoder", lanes, tensors, offsets=None,
+                          max_num_frames: int = -1) -> None:
+    """`BatchFasterDecoder.advance_decoding` for log-probs that already live on the GPU.
+
+    `tensors[i]` is a contiguous float32 `[T_i, V]` CUDA array for lane `lanes[i]`: a torch
+    tensor, or anything exposing `__cuda_array_interface__` (CuPy, Numba).  No copy is made and
+    the call returns when the frames are decoded, so the arrays only have to outlive the call.
+    """
+    ptrs, rows, cols = [], [], None
+    for t in tensors:
+        if hasattr(t, "data_ptr"):  # torch
+            if not t.is_cuda or str(t.dtype) != "torch.float32" or not t.is_contiguous() or t.dim() != 2:
+                raise ValueError("expected contiguous float32 [T, V] CUDA tensors")
+            ptr, shape = int(t.data_ptr()), tuple(t.shape)
+        else:
+            cai = t.__cuda_array_interface__
+            if cai["typestr"] not in ("<f4", "=f4") or len(cai["shape"]) != 2 or cai.get("strides"):
+                raise ValueError("expected contiguous float32 [T, V] CUDA arrays")
+            ptr, shape = int(cai["data"][0]), tuple(cai["shape"])
+        if cols is None:
+            cols = int(shape[1])
+        elif cols != int(shape[1]):
+            raise ValueError("all matrices must have the same number of columns")
+        ptrs.append(ptr)
+        rows.append(int(shape[0]))
+    decoder.advance_decoding_ptrs(list(lanes), ptrs, rows, int(cols or 0),
+                                  list(offsets) if offsets is not None else [],
+                                  int(max_num_frames), True)

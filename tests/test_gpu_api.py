@@ -336,3 +336,26 @@ def test_path_batch_views_and_copies():
     dec.best_paths([2])
     for a, k in zip(owned, keep):
         assert np.array_equal(a.ilabels, k)
+
+
+def test_cuda_tensors_are_decoded_in_place():
+    """kaldi_decoder.advance_decoding_cuda: torch CUDA tensors, no host copy; same result as
+    the numpy path."""
+    import torch
+    import kaldi_decoder as kd
+    g = small_graph("HLG")
+    fst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                      g.weight, g.nextstate, g.final)
+    bd = kd.BatchFasterDecoder(fst, kd.FasterDecoderOptions(beam=12.0, max_active=300), 4)
+    mats = [synth.make_logprobs(g, 50 + 7 * u, seed=90 + u, peak=7) for u in range(2)]
+    bd.init_decoding([0, 1, 2, 3])
+    bd.advance_decoding([0, 1], mats)
+    kd.advance_decoding_cuda(bd, [2, 3], [torch.from_numpy(m).cuda() for m in mats])
+    oks, lats = bd.get_best_paths([0, 1, 2, 3])
+    assert all(oks)
+    seqs = [kd.get_linear_symbol_sequence(l) for l in lats]
+    for u in range(2):
+        assert list(seqs[u][1]) == list(seqs[u + 2][1]) and list(seqs[u][2]) == list(seqs[u + 2][2])
+        assert seqs[u][3] == seqs[u + 2][3]
+    with pytest.raises(ValueError):
+        kd.advance_decoding_cuda(bd, [0], [torch.zeros(3, 4)])
