@@ -198,10 +198,6 @@ __device__ __forceinline__ float funkey(uint32_t k) {
 // (measured 108.8 -> 103.5 ms per launch).
 __device__ __forceinline__ double widen(float f) { return static_cast<double>(f); }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 __device__ __forceinline__ HVal ld_hval(const HVal *p) {
   ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
   HVal r;
@@ -424,17 +420,6 @@ __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B
                                                uint32_t *eps_queue_n) {
   const uint32_t h = table_hash(P, state);
   return table_slot_from(P, B, sh, state, h, __ldcg(&B.table[h].key), eps_queue, eps_queue_n);
-}
-
-// Emitting-phase recombination: keep the lexicographic minimum of (cost, arg).
-// Most arrivals at an occupied slot do not improve it: they cost one load.
-__device__ __forceinline__ void table_min(HVal *slot, HVal mine) {
-  HVal cur = ld_hval(slot);
-  while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
-    HVal got = cas_hval(slot, cur, mine);
-    if (got.cost == cur.cost && got.arg == cur.arg) return;
-    cur = got;
-  }
 }
 
 // Block-wide count of tokens with float(cost) <= bound (used to skip the exact
