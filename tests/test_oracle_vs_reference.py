@@ -140,3 +140,39 @@ def test_simple_mode_matches_reference_simple_decoder(gname, beam, peak):
         if f < mat.shape[0]:
             orc.advance_decoding(mat, 0, 1)
             ref.advance_decoding(mat, 0, 1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_simple_mode_random_fsts(seed):
+    """Unstructured graphs (negative weights, epsilon chains, non-determinism): oracle mode 2 vs
+    the reference SimpleDecoder after every frame."""
+    import math
+    g = synth.make_random_fst(num_states=100 + 30 * seed, num_arcs=1200 + 200 * seed, vocab=20,
+                              eps_frac=0.1 + 0.02 * seed, seed=300 + seed)
+    rng = np.random.default_rng(seed)
+    T = 40
+    x = rng.standard_normal((T, 20)).astype(np.float32) * np.float32(1.5)
+    x[np.arange(T), rng.integers(0, 20, size=T)] += np.float32(4.0)
+    x -= np.log(np.exp(x).sum(axis=1, keepdims=True))
+    mat = x.astype(np.float32)
+    beam = [4.0, 7.0, 11.0][seed % 3]
+    orc = kd_oracle.OracleDecoder(kd_oracle.OracleGraph(g), kd_ref.Options(beam=beam),
+                                  kd_oracle.SIMPLE)
+    ref = kd_ref.RefSimpleDecoder(kd_ref.RefGraph(g), beam)
+    orc.init_decoding()
+    ref.init_decoding()
+    fin = np.asarray(g.final)
+    for f in range(T + 1):
+        assert orc.reached_final() == ref.reached_final(), f
+        st, co = orc.tokens()
+        a, b = _frc(st, co, fin), ref.final_relative_cost()
+        assert (math.isinf(a) and math.isinf(b)) or abs(a - b) <= 1e-4 * max(1.0, abs(b)), (f, a, b)
+        p, r = orc.get_best_path(True), ref.get_best_path(True)
+        assert p.ok == r.ok, f
+        if r.ok:
+            assert rel_close(p.total_cost, r.total_cost, 1e-5), (f, p.total_cost, r.total_cost)
+            if not (np.array_equal(p.isyms, r.isyms) and np.array_equal(p.osyms, r.osyms)):
+                assert p.total_cost == pytest.approx(r.total_cost, rel=1e-6)
+        if f < T:
+            orc.advance_decoding(mat, 0, 1)
+            ref.advance_decoding(mat, 0, 1)
