@@ -139,3 +139,34 @@ def test_simple_search_token_sets_equal_the_oracle_every_frame(gname, beam, peak
         assert rel_close(p.total_cost, o.total_cost, 1e-6)
         if np.array_equal(p.ilabels, o.ilabels):
             assert np.array_equal(p.graph, o.graph) and np.array_equal(p.acoustic, o.acoustic)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_simple_search_random_fsts_token_sets(seed):
+    """Random graphs with negative weights and epsilon chains: device token list == oracle
+    mode 2 after every frame (states and bit-identical costs)."""
+    g = synth.make_random_fst(num_states=120 + 40 * seed, num_arcs=1500 + 300 * seed, vocab=20,
+                              eps_frac=0.1 + 0.03 * seed, seed=500 + seed)
+    rng = np.random.default_rng(100 + seed)
+    T = 40
+    x = rng.standard_normal((T, 20)).astype(np.float32) * np.float32(1.5)
+    x[np.arange(T), rng.integers(0, 20, size=T)] += np.float32(4.0)
+    x -= np.log(np.exp(x).sum(axis=1, keepdims=True))
+    mat = x.astype(np.float32)
+    beam = [5.0, 8.0, 12.0, 6.5][seed]
+    dg = capi.DeviceGraph.from_graph(g)
+    dec = capi.LaneDecoder(dg, capi.make_options(beam=beam), max_lanes=1,
+                           search=capi.KD_SEARCH_SIMPLE, hash_capacity=1 << 16,
+                           arena_records=1 << 19)
+    orc = kd_oracle.OracleDecoder(kd_oracle.OracleGraph(g), kd_ref.Options(beam=beam),
+                                  kd_oracle.SIMPLE)
+    dec.init([0])
+    orc.init_decoding()
+    for f in range(T + 1):
+        gs, gc = sorted_tokens(*dec.tokens(0))
+        os_, oc = sorted_tokens(*orc.tokens())
+        assert np.array_equal(gs, os_), (seed, f, len(gs), len(os_))
+        assert np.array_equal(gc, oc), (seed, f)
+        if f < T:
+            dec.advance([0], [mat], max_num_frames=1)
+            orc.advance_decoding(mat, 0, 1)
