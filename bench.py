@@ -64,13 +64,15 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--check", action="store_true", help="compare a sample with the reference")
+    ap.add_argument("--groups", type=int, default=2,
+                    help="lane groups taking turns (2: steps are enqueued one ahead; 1: sequential)")
     return ap.parse_args()
 
 
 CONFIG_LANES = {"C1": 64, "C2": 256, "C3": 1024, "C4": 1024}
 # tokens alive in one frame must stay below half of this (measured maxima: C1 500, C2 146k,
 # C3 49k, C4 142k tokens)
-CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 20, "C3": 1 << 18, "C4": 1 << 20}
+CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 20, "C3": 1 << 18, "C4": 1 << 19}
 CONFIG_NAME = {
     "C1": "H-500 CTC topology, 64 utts x T=1000 x V=500, beam 20, max_active 7000",
     "C2": "HL 200k-word lexicon trie, 256 utts x T=1000 x V=500, beam 20, max_active 7000",
@@ -167,10 +169,29 @@ def make_device_logprobs(g, n_utts, T, seed, peak, device):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of kd_advance_kernel from the committed
-# `ncu --set full` capture (profiles/r1_final_ncu_summary.txt: 9.58 + 6.72 GB for a launch of
-# 1024 lanes x 100 frames of this workload), per lane-frame.  Only valid for config C3.
-NCU_DRAM_BYTES_PER_LANE_FRAME_C3 = (9.580444e9 + 6.723989e9) / (1024 * 100)
+def measured_traffic(config: str, peak: float, lanes: int, T: int):
+    """DRAM bytes per launch of kd_advance_kernel, scaled from the ncu capture of this build
+    kept in profiles/r2_dram_bytes.json ({config: {"peak": p, "bytes_per_lane_frame": b}})."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_bytes.json")) as f:
+            rec = json.load(f).get(config)
+        if rec and float(rec.get("peak", 12.0)) == float(peak):
+            return float(rec["bytes_per_lane_frame"]) * lanes * T
+    except Exception:
+        pass
+    return None
+
+
+def touched_bytes(st: dict, cols: int) -> float:
+    """Bytes the kernel actually requests (not the out-degree formula of SURVEY 8(d)): arcs
+    that label tables skip are not counted, table traffic is."""
+    return (8.0 * st["arcs_evaluated"]
+            + st["candidates"] * (16.0 + 16.0 + 8.0 + 32.0)
+            + st["slots_claimed"] * (32.0 + 4.0 + 4.0)
+            + st["tokens_in"] * (12.0 + 32.0)
+            + st["tokens_out"] * 20.0
+            + st["eps_arcs"] * (16.0 + 32.0)
+            + 4.0 * cols * st["frames"])
 
 
 def algorithmic_bytes(st: dict, cols: int) -> float:
@@ -246,7 +267,12 @@ def main():
     g = synth.make_config_graph(args.config)
     V = int(g.lm["vocab"])
     dg = capi.DeviceGraph.from_graph(g, device=local_rank)
-    dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes,
+    # Two lane groups take turns: step k decodes its utterances in group k % 2.  The steps
+    # are enqueued one ahead (kd_decoder_advance_async), so the lanes of step k+1 take over
+    # the SMs as the slowest lanes of step k finish, and (end to end) the upload of step k+1
+    # runs under the search of step k.  --groups 1 gives strictly sequential steps.
+    n_groups = max(1, args.groups)
+    dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes * n_groups,
                            hash_capacity=args.hash_capacity or CONFIG_HASH[args.config],
                            arena_records=args.arena_records,
                            threads_per_lane=args.threads_per_lane,
@@ -254,7 +280,7 @@ def main():
     # every rank decodes its own utterances (seed differs per rank): weak scaling
     logp = make_device_logprobs(g, lanes, T, args.seed + 7919 * rank, args.peak, dev)
     torch.cuda.synchronize()
-    lane_ids = list(range(lanes))
+    groups = [list(range(k * lanes, (k + 1) * lanes)) for k in range(n_groups)]
     rows = [T] * lanes
     dptrs = [logp[u].data_ptr() for u in range(lanes)]
     host = None
@@ -265,66 +291,78 @@ def main():
         hptrs = [host[u].data_ptr() for u in range(lanes)]
     setup_s = time.time() - t_setup
 
-    kernel_ms = []
     result = {}
 
-    def step_device():
-        dec.init(lane_ids)
-        dec.advance_ptrs(lane_ids, dptrs, rows, V, None, -1, capi.KD_MEM_DEVICE)
-        kernel_ms.append(dec.last_advance_info()[0])
-        # zero-copy result (views of the decoder's pinned buffer, consumed before the next call)
-        result["paths"] = dec.best_paths(lane_ids, True, copy=False)
+    def run_steps(ptrs, mem_kind, steps):
+        """`steps` steps, each = InitDecoding + AdvanceDecoding over all frames + GetBestPath of
+        `lanes` utterances in ONE kernel launch; step k+1 is enqueued before step k's paths
+        are read (when there is more than one lane group)."""
+        pending = []
+        for k in range(steps):
+            t = dec.advance_async(groups[k % n_groups], ptrs, rows, V, None, -1, mem_kind,
+                                  init=True, finalize=True)
+            pending.append(t)
+            if len(pending) >= n_groups:
+                # zero-copy result (views of the decoder's pinned buffer)
+                result["paths"] = dec.results(pending.pop(0), True, copy=False)
+        while pending:
+            result["paths"] = dec.results(pending.pop(0), True, copy=False)
 
-    def step_host():
-        dec.init(lane_ids)
-        dec.advance_ptrs(lane_ids, hptrs, rows, V, None, -1, capi.KD_MEM_HOST)
-        result["paths"] = dec.best_paths(lane_ids, True, copy=False)
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
+    def timed(ptrs, mem_kind, steps, warmup):
+        if warmup:
+            run_steps(ptrs, mem_kind, warmup)
         barrier()
+        dec.span_begin()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            fn()
+        run_steps(ptrs, mem_kind, steps)
+        span_ms, n_launch = dec.span_end()
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        return dt
+        return dt, span_ms, n_launch
 
+    # one launch alone (nothing else on the GPU): its CUDA-event duration
+    run_steps(dptrs, capi.KD_MEM_DEVICE, 1)
+    single_ms = dec.last_advance_info()[0]
     sampler = ClockSampler(local_rank)
-    kernel_ms.clear()
-    for _ in range(args.warmup):
-        step_device()
-    kernel_ms.clear()
+    timed(dptrs, capi.KD_MEM_DEVICE, 0, args.warmup)
     sampler.start()
-    dt = timed(step_device, args.steps, 0)
+    dt, span_ms, n_launch = timed(dptrs, capi.KD_MEM_DEVICE, args.steps, 0)
     clocks = sampler.stop()
-    st = dec.stats()  # counters of the last step (kd_decoder_init resets them)
+    st = dec.stats()  # counters of the last step of every lane group (InitDecoding resets them)
+    for k in st:
+        if k != "max_tokens":
+            st[k] //= min(n_groups, args.steps + args.warmup + 1)
     ms_per_step = dt / args.steps * 1e3
     frames_per_step = lanes * T * world
     value = frames_per_step / (dt / args.steps)
-    k_ms = sum(kernel_ms) / max(1, len(kernel_ms))
+    # launches of consecutive steps overlap: the device time per launch is the span from the
+    # first launch's start to the last one's end, over the number of launches
+    k_ms = span_ms / max(1, n_launch)
     peak_gbs, peak_src = measured_peaks()
     alg_bytes = algorithmic_bytes(st, V)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    touched = touched_bytes(st, V)
     paths = result["paths"]
-    d2h = int(paths.ilabels.nbytes * 4) + 8 * lanes
+    d2h = int(paths.d2h_bytes) + int(lanes * 256)  # parked paths + lane states
     n_final = int(np.count_nonzero(paths.reached_final))
     # label sequences of the timed device-input step, kept for the parity sample below (the
-    # views are overwritten by the next best_paths call)
+    # views are overwritten by later calls)
     n_keep = min(lanes, args.cpu_sample_utts or max(2 * cores, 16))
-    kept = [(paths[u].isyms.copy(), paths[u].osyms.copy()) for u in range(n_keep)]
+    kept = [(paths[u].isyms.copy(), paths[u].osyms.copy(), paths[u].total_cost,
+             bool(paths[u].reached_final)) for u in range(n_keep)]
+    gpu_launches = n_launch
 
     e2e = None
     if not args.no_e2e:
-        dt_h = timed(step_host, args.steps, max(1, args.warmup))
+        dt_h, span_h, n_launch_h = timed(hptrs, capi.KD_MEM_HOST, args.steps, max(1, args.warmup))
         e2e = {"value": frames_per_step / (dt_h / args.steps), "unit": UNIT,
                "h2d_bytes_per_step": int(lanes * T * V * 4), "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt_h / args.steps * 1e3}
+               "ms_per_step": dt_h / args.steps * 1e3,
+               "kernel_span_ms_per_step": span_h / max(1, n_launch_h)}
 
     cpu = None
     check = None
@@ -339,13 +377,41 @@ def main():
             cpu = {"value": n_s * T / secs, "unit": UNIT, "cores": cores, "kind": "reference",
                    "sample": f"first {n_s} utterances x {T} frames of the same batch, "
                              f"{cores} threads, oracle/_ref (unmodified faster-decoder.cc)"}
-            # parity of the sample (not timed): label sequences vs the reference
-            same = 0
+            # parity of the sample (not timed), SURVEY.md section 8(d): label sequences vs the
+            # reference; a divergent utterance is an exact tie if its total cost equals the
+            # reference's (1e-4 relative is the stated tolerance; ties agree to fp32 rounding)
+            # and real otherwise; split by whether GetCutoff ever returned through
+            # max_active / min_active on that utterance (oracle counters, reference order)
+            from oracle import kd_oracle
+            og = kd_oracle.OracleGraph(g)
+            _, _, _, _, per = kd_oracle.decode_batch(og, sample_mats, kd_ref.Options(**OPTS), cores,
+                                                     mode=kd_oracle.REFERENCE_ORDER, want_paths=False)
+            names = list(kd_oracle.STAT_NAMES)
+            bmax = per[:, names.index("binding_max")]
+            check = {"utterances": n_s, "identical_label_sequences": 0,
+                     "max_active_binding_utts": int((bmax > 0).sum()),
+                     "max_active_binding_frames": int(bmax.sum()),
+                     "min_active_binding_frames": int(per[:, names.index("binding_min")].sum()),
+                     "never_binding": {"utts": 0, "identical": 0, "ties": 0, "real": 0},
+                     "binding": {"utts": 0, "identical": 0, "ties": 0, "real": 0},
+                     "max_rel_cost_diff": 0.0, "reached_final_mismatch": 0}
             for u in range(n_s):
-                if (np.array_equal(kept[u][0], rpaths[u].isyms)
-                        and np.array_equal(kept[u][1], rpaths[u].osyms)):
-                    same += 1
-            check = {"utterances": n_s, "identical_label_sequences": same}
+                cls = check["binding" if bmax[u] > 0 else "never_binding"]
+                cls["utts"] += 1
+                same = (np.array_equal(kept[u][0], rpaths[u].isyms)
+                        and np.array_equal(kept[u][1], rpaths[u].osyms))
+                rc_ = rpaths[u].total_cost
+                rel = abs(kept[u][2] - rc_) / max(1.0, abs(rc_))
+                check["max_rel_cost_diff"] = max(check["max_rel_cost_diff"], rel)
+                if kept[u][3] != bool(rrf[u]):
+                    check["reached_final_mismatch"] += 1
+                if same:
+                    cls["identical"] += 1
+                    check["identical_label_sequences"] += 1
+                elif rel <= 1e-6:
+                    cls["ties"] += 1
+                else:
+                    cls["real"] += 1
 
     if rank == 0:
         line = {
@@ -357,19 +423,38 @@ def main():
                        "options": OPTS, "parallelism": f"replicas x{world} (utterances sharded)",
                        "l2_policy": "inputs larger than L2 (log-probs %.2f GB per GPU)" % (lanes * T * V * 4 / 1e9),
                        "threads_per_lane": dec.info()["threads_per_lane"],
+                       "lane_groups": n_groups,
+                       "pipelining": ("step k+1 enqueued before step k's paths are read; one "
+                                      "kernel launch per step (InitDecoding + all frames + "
+                                      "GetBestPath)") if n_groups > 1 else "none",
                        "reached_final": n_final},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs,
-                         "traffic": (NCU_DRAM_BYTES_PER_LANE_FRAME_C3 * lanes * T
-                                     if args.config == "C3" and args.peak == 12.0 else None),
-                         "traffic_note": "DRAM bytes per launch scaled from the ncu capture in "
-                                         "profiles/r1_final_ncu_summary.txt (per lane-frame x lanes x frames)",
+                         "traffic": measured_traffic(args.config, args.peak, lanes, T),
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
+                                         "--set full capture of this build "
+                                         "(profiles/r2_dram_bytes.json, per lane-frame x lanes x "
+                                         "frames); null = no capture for this config",
                          "kernel": "kd_advance_kernel", "kernel_ms": k_ms,
-                         "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                         "counters": st},
+                         "kernel_ms_note": "launches of consecutive steps overlap: (end of the "
+                                           "last launch - start of the first) / launches, CUDA "
+                                           "events on the launching streams, timed region",
+                         "kernel_ms_alone": single_ms,
+                         "frac_alone": (alg_bytes / (single_ms * 1e-3) / 1e9 / peak_gbs
+                                        if single_ms > 0 else None),
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "touched_bytes_per_launch": touched,
+                         "touched_frac": touched / (k_ms * 1e-3) / 1e9 / peak_gbs if k_ms > 0 else None,
+                         "touched_note": "bytes the kernel requests, from its own counters: arcs "
+                                         "evaluated (8 B scanned, 8 B looked up), candidates "
+                                         "(16 B written + read, 8 B arc record, 32 B table sector), "
+                                         "slots claimed (32 B wipe, 4 B list), tokens in "
+                                         "(12 B + 32 B state record) / out (20 B), epsilon arcs "
+                                         "(16 B + 32 B sector), the row",
+                         "peak_source": peak_src, "counters": st},
             "cpu_baseline": cpu,
             "parity_sample": check,
             "setup_s": setup_s,

@@ -149,6 +149,56 @@ KD_API int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
                               int32_t cols, const int32_t *offsets,
                               int32_t max_num_frames, int mem_kind);
 
+/* ---- the same call without waiting, and with InitDecoding / GetBestPath folded in.
+ *
+ * kd_decoder_advance_async enqueues the call and returns; kd_decoder_wait(ticket) completes
+ * it and reports its outcome (ticket < 0: every call in flight).  Up to three calls on
+ * disjoint lanes are in flight at once, each on its own streams: the upload and the search
+ * of one batch of lanes overlap the search and the download of another, and the lanes of
+ * the next batch take over the SMs as the slowest lanes of the previous one finish.  Any
+ * other call that touches a lane first completes the call that owns it (deferred
+ * synchronisation), so the synchronous API can be mixed in freely.  Host matrices must
+ * stay valid and unchanged until the call has completed.
+ *
+ * flags:
+ *   KD_ADVANCE_INIT      InitDecoding (faster-decoder.cc:42-56) of every listed lane first,
+ *                        inside the same kernel launch.
+ *   KD_ADVANCE_FINALIZE  after the last frame, select each lane's best path
+ *                        (faster-decoder.cc:356-402) inside the same launch and bring its
+ *                        arcs back behind it: kd_decoder_result_view then needs no kernel,
+ *                        and kd_decoder_best_path_* / kd_decoder_reached_final on these
+ *                        lanes reuse the selection.
+ * With both flags a whole Decode() + GetBestPath() of a batch is ONE kernel launch.
+ *
+ * producer_stream (KD_MEM_DEVICE only): the CUDA stream (cudaStream_t) on which the work
+ * producing the matrices was enqueued; the search is ordered behind it.  NULL means the
+ * legacy default stream (which in turn waits for all blocking streams).  The decoder's own
+ * streams are non-blocking: without this ordering a log_softmax still running on another
+ * stream would race with the search.  kd_decoder_advance orders behind the legacy default
+ * stream. */
+#define KD_ADVANCE_INIT 1
+#define KD_ADVANCE_FINALIZE 2
+KD_API int kd_decoder_advance_async(kd_decoder *d, int32_t n, const int32_t *lanes,
+                                    const float *const *logprobs, const int32_t *rows,
+                                    int32_t cols, const int32_t *offsets,
+                                    int32_t max_num_frames, int mem_kind, int flags,
+                                    void *producer_stream, int64_t *ticket);
+KD_API int kd_decoder_wait(kd_decoder *d, int64_t ticket);
+
+/* The best paths of a KD_ADVANCE_FINALIZE call (completes it if it is still in flight).
+ * *lanes lists the *num_lanes lanes the call advanced, in call order; lane i's arcs are
+ * four arrays of num_arcs[i] words -- ilabel, olabel (int32), graph cost, acoustic cost
+ * (float) -- starting at (*words)[(*word_offsets)[4 * i + 0..3]].  The pointers address
+ * pinned host memory of the decoder and stay valid until the third-next
+ * kd_decoder_advance_async call or the decoder's destruction.  ok / reached_final /
+ * final_weight2 (2 per lane) as kd_decoder_best_path_prepare / _fetch; any may be NULL,
+ * arrays must hold *num_lanes entries (at most the n of the call). */
+KD_API int kd_decoder_result_view(kd_decoder *d, int64_t ticket, int use_final_probs,
+                                  int32_t *num_lanes, const int32_t **lanes,
+                                  const int32_t **words, const int64_t **word_offsets,
+                                  int64_t *num_arcs, int32_t *ok, int32_t *reached_final,
+                                  float *final_weight2);
+
 /* FasterDecoder::NumFramesDecoded (faster-decoder.h:107); -1 before init. */
 KD_API int kd_decoder_num_frames_decoded(kd_decoder *d, int32_t lane, int32_t *out);
 
@@ -202,6 +252,14 @@ KD_API int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out);
 /* Device time (ms, CUDA events on the decoder's streams) of the search kernels
  * of the last kd_decoder_advance call, and how many kernels it launched. */
 KD_API int kd_decoder_last_advance_info(kd_decoder *d, float *kernel_ms, int32_t *launches);
+
+/* Device time of a run of search launches that may overlap (calls in flight on several
+ * streams): kd_decoder_span_begin arms the measurement, the next launch opens it;
+ * kd_decoder_span_end completes every call in flight and returns the CUDA-event time from
+ * the start of the first launch to the end of the most recently enqueued one, and the
+ * number of search kernels launched in between. */
+KD_API int kd_decoder_span_begin(kd_decoder *d);
+KD_API int kd_decoder_span_end(kd_decoder *d, float *ms, int32_t *launches);
 
 /* info[0..5] = max_lanes, hash_capacity, arena_records, threads_per_lane,
  *              device bytes allocated, chunk_frames */

@@ -37,7 +37,7 @@ int Fail(int code, const std::string &msg) {
     }                                                                              \
   } while (0)
 
-constexpr int kNumStreams = 8;
+constexpr int kNumSlots = 3;  // asynchronous calls in flight per decoder
 constexpr int kNumSMsFallback = 148;
 
 template <class T>
@@ -66,11 +66,45 @@ struct kd_graph {
   float *fin = nullptr;
 };
 
+// One asynchronous AdvanceDecoding call in flight: its own streams, staging buffer, item
+// list, progress words and result buffer, so that the upload and the search of one batch of
+// lanes overlap the search and the download of another.
+struct kd_slot {
+  cudaStream_t sc = nullptr, sx = nullptr;  // search, copy
+  cudaEvent_t ev_gate = nullptr, ev_begin = nullptr, ev_end = nullptr, ev_dep = nullptr;
+  kd::AdvanceItem *d_items = nullptr, *h_items = nullptr;  // max_lanes each
+  int32_t *d_words = nullptr;     // [0] work counter, [1] yield flag, [2] rows delivered
+  int32_t *h_progress = nullptr;  // pinned: one value per chunk
+  int32_t progress_cap = 0;
+  float *d_stage = nullptr;       // host-memory advance: the lanes' rows on the device
+  size_t stage_floats = 0;
+  int32_t *h_res = nullptr;       // pinned: parked best paths, [lane][4 * path_cap] words (+ spill)
+  size_t res_words = 0;
+  long long *d_out_off = nullptr, *h_out_off = nullptr;  // spill of unparked paths
+  // the call in flight
+  bool busy = false;
+  int64_t ticket = -1;
+  int rc = 0;                 // outcome of the last completed call
+  std::string msg;
+  std::vector<int32_t> lanes, targets;
+  kd::Params P;
+  int threads = 0;
+  int flags = 0;
+  int32_t path_cap = 0;
+  bool host_input = false;
+  bool res_valid = false;     // h_res holds the results of `ticket`
+  std::vector<int64_t> res_off;  // [4n] word offsets into h_res
+  float kernel_ms = 0.f;
+  int32_t launches = 0;
+};
+
 struct kd_decoder {
   kd_graph *g = nullptr;
   kd_options opts;
   int device = 0;
   int num_sms = kNumSMsFallback;
+  size_t mem_pitch = 0;
+  bool launch_blocking = false;
   int32_t max_lanes = 1;
   uint32_t hcap = 0, lcap = 0, qcap = 0, ccap = 0;
   int64_t arena_cap = 0;
@@ -89,17 +123,10 @@ struct kd_decoder {
   uint32_t *queue = nullptr;
   uint4 *cand = nullptr;
   uint4 *front = nullptr;
-  kd::AdvanceItem *d_items = nullptr;
-  int32_t *d_progress = nullptr;  // rows delivered by the copy stream (host-memory advance)
-  int32_t *h_progress = nullptr;  // pinned: one value per chunk
-  int32_t progress_cap = 0;
-  int32_t *d_counters = nullptr;  // one per launch slot
-  int32_t n_counters = 0;
+  kd::AdvanceItem *d_items = nullptr;  // synchronous helpers (init, best path, ...)
   long long *d_out_off = nullptr;
+  int32_t *d_flags = nullptr;          // ReachedFinal results, max_lanes
 
-  // growable device scratch
-  float *d_stage = nullptr;
-  size_t stage_floats = 0;
   int32_t *d_path = nullptr;  // best paths: [ilabel | olabel | graph | acoustic], path_cap words each
   int32_t *h_path = nullptr;  // pinned mirror
   int64_t path_cap = 0;
@@ -108,15 +135,23 @@ struct kd_decoder {
   kd::AdvanceItem *h_items = nullptr;
   kd::LaneState *h_lanes = nullptr;
   long long *h_out_off = nullptr;
+  int32_t *h_flags = nullptr;
 
   std::vector<int32_t> frames;  // host mirror of num_frames_decoded_, -1 = not initialised
   std::vector<int32_t> status;
-  std::vector<uint8_t> bp_valid;  // best_path_prepare ran for the lane's current tokens
-  int last_use_final = 1;
+  std::vector<uint8_t> bp_valid;   // the lane's best path is selected for its current tokens
+  std::vector<uint8_t> use_final;  // per lane: use_final_probs of its last best-path request
+  std::vector<int8_t> rf_cache;    // per lane: ReachedFinal of its current tokens, -1 = unknown
+  std::vector<int8_t> lane_slot;   // per lane: slot of the call in flight that owns it, -1 = none
 
-  cudaStream_t streams[kNumStreams] = {};
-  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-  cudaEvent_t ev_stream[kNumStreams] = {};
+  kd_slot slots[kNumSlots];
+  int64_t next_ticket = 0;
+  // timing span over several (overlapping) launches: begin = before the first launch after
+  // kd_decoder_span_begin, end = behind the most recently enqueued launch
+  cudaEvent_t ev_span_begin = nullptr, ev_span_end = nullptr;
+  bool span_armed = false, span_open = false;
+  int32_t span_launches = 0;
+  cudaStream_t stream = nullptr;   // synchronous helpers
   float last_kernel_ms = 0.f;
   int32_t last_launches = 0;
   int32_t last_blocks_per_sm = 0;
@@ -203,7 +238,6 @@ int LaunchAdvanceR(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s) {
   int grid = std::min(n_items, per_sm * d->num_sms);
   kd::kd_advance_kernel<THREADS, MIN_BLOCKS, ROW_SMEM><<<grid, THREADS, smem, s>>>(P);
   KD_CUDA(cudaGetLastError());
-  d->last_launches++;
   d->last_blocks_per_sm = per_sm;
   return KD_OK;
 }
@@ -230,7 +264,6 @@ int LaunchAdvanceSimple(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s
     const int grid = std::min(n_items, per_sm * d->num_sms);
     kernel<<<grid, THREADS, smem, s>>>(P);
     KD_CUDA(cudaGetLastError());
-    d->last_launches++;
     d->last_blocks_per_sm = per_sm;
     return KD_OK;
   };
@@ -291,7 +324,7 @@ int CheckLanes(const kd_decoder *d, int32_t n, const int32_t *lanes) {
 }
 
 // Pulls the device lane states of `lanes` into the pinned mirror.
-int FetchLaneStates(kd_decoder *d, int32_t n, const int32_t *lanes) {
+int FetchLaneStates(kd_decoder *d, int32_t n, const int32_t *lanes, cudaStream_t s, bool sync = true) {
   if (n == 0) return KD_OK;
   int32_t lo = lanes[0], hi = lanes[0];
   for (int32_t i = 1; i < n; ++i) {
@@ -300,8 +333,8 @@ int FetchLaneStates(kd_decoder *d, int32_t n, const int32_t *lanes) {
   }
   KD_CUDA(cudaMemcpyAsync(d->h_lanes + lo, d->lanes + lo,
                           sizeof(kd::LaneState) * static_cast<size_t>(hi - lo + 1),
-                          cudaMemcpyDeviceToHost, d->streams[0]));
-  KD_CUDA(cudaStreamSynchronize(d->streams[0]));
+                          cudaMemcpyDeviceToHost, s));
+  if (sync) KD_CUDA(cudaStreamSynchronize(s));
   return KD_OK;
 }
 
@@ -466,17 +499,22 @@ int kd_graph_create(int device, int32_t num_states, int32_t start, const int64_t
   g->n_arc = reinterpret_cast<int4 *>(g->blob + b_iw + b_st + b_no);
   g->fin = reinterpret_cast<float *>(g->blob + b_iw + b_st + b_no + b_na);
   g->labtab = reinterpret_cast<int2 *>(g->blob + b_iw + b_st + b_no + b_na + b_fin);
-  if (!labtab.empty())
-    KD_CUDA(cudaMemcpy(g->labtab, labtab.data(), labtab.size() * sizeof(int2),
-                       cudaMemcpyHostToDevice));
-  KD_CUDA(cudaMemcpy(g->st, st.data(), st.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  if (!eiw.empty()) {
-    KD_CUDA(cudaMemcpy(g->e_iw, eiw.data(), eiw.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    KD_CUDA(cudaMemcpy(g->e_no, eno.data(), eno.size() * sizeof(int2), cudaMemcpyHostToDevice));
+  auto upload = [&](void *dst, const void *src, size_t bytes) -> int {
+    if (bytes == 0) return KD_OK;
+    KD_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return KD_OK;
+  };
+  if ((rc = upload(g->labtab, labtab.data(), labtab.size() * sizeof(int2))) ||
+      (rc = upload(g->st, st.data(), st.size() * sizeof(int4))) ||
+      (rc = upload(g->e_iw, eiw.data(), eiw.size() * sizeof(int2))) ||
+      (rc = upload(g->e_no, eno.data(), eno.size() * sizeof(int2))) ||
+      (rc = upload(g->n_arc, na.data(), na.size() * sizeof(int4))) ||
+      (rc = upload(g->fin, final_weight, sizeof(float) * num_states))) {
+    const std::string keep = g_error;
+    kd_graph_destroy(g);
+    g_error = keep;
+    return rc;
   }
-  if (!na.empty())
-    KD_CUDA(cudaMemcpy(g->n_arc, na.data(), na.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  KD_CUDA(cudaMemcpy(g->fin, final_weight, sizeof(float) * num_states, cudaMemcpyHostToDevice));
   *out = g;
   return KD_OK;
 }
@@ -510,14 +548,39 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   kd_decoder_config c;
   memset(&c, 0, sizeof(c));
   if (cfg) c = *cfg;
+  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 &&
+      c.threads_per_lane != 192 && c.threads_per_lane != 224 && c.threads_per_lane != 256 &&
+      c.threads_per_lane != 384 && c.threads_per_lane != 512)
+    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 224, 256, 384 or 512");
+  if (c.search != KD_SEARCH_FASTER && c.search != KD_SEARCH_SIMPLE)
+    return Fail(KD_ERR_INVALID,
+                "kd_decoder_config.search must be KD_SEARCH_FASTER or KD_SEARCH_SIMPLE");
   auto *d = new kd_decoder;
+  // (every early return below goes through kd_decoder_destroy: nothing leaks)
+  auto fail = [&](int code) {
+    const std::string keep = g_error;
+    kd_decoder_destroy(d);
+    g_error = keep;
+    return code;
+  };
+#define KD_CUDA_D(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t kd_e_ = (expr);                                                              \
+    if (kd_e_ != cudaSuccess)                                                                \
+      return fail(Fail(KD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(kd_e_))); \
+  } while (0)
   d->g = g;
   d->opts = *opts;
   d->device = g->device;
   d->max_lanes = c.max_lanes > 0 ? c.max_lanes : 1;
   cudaDeviceProp prop;
-  KD_CUDA(cudaGetDeviceProperties(&prop, g->device));
+  KD_CUDA_D(cudaGetDeviceProperties(&prop, g->device));
   d->num_sms = prop.multiProcessorCount;
+  d->mem_pitch = prop.memPitch;
+  {
+    const char *e = getenv("CUDA_LAUNCH_BLOCKING");
+    d->launch_blocking = e != nullptr && e[0] != '\0' && e[0] != '0';
+  }
   // Default table size: the largest power of two that keeps all lanes' tables (and their
   // slot lists, worklists, candidate buffers: 48 bytes per entry) within ~15% of the free
   // device memory, between 2^15 and 2^22 entries.  A frame may hold capacity / 2 tokens.
@@ -526,7 +589,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
     hcap = static_cast<uint32_t>(c.hash_capacity);
   } else {
     size_t free_b = 0, total_b = 0;
-    KD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    KD_CUDA_D(cudaMemGetInfo(&free_b, &total_b));
     const double per_lane = 0.15 * static_cast<double>(free_b) / d->max_lanes / 48.0;
     hcap = 1u << 15;
     while (hcap < (1u << 22) && 2.0 * hcap <= per_lane) hcap <<= 1;
@@ -537,16 +600,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->lcap = p2 / 2;
   d->qcap = p2;
   d->ccap = p2 / 4;
-  if (c.threads_per_lane != 0 && c.threads_per_lane != 128 && c.threads_per_lane != 160 && c.threads_per_lane != 192 && c.threads_per_lane != 224 &&
-      c.threads_per_lane != 256 && c.threads_per_lane != 384 && c.threads_per_lane != 512) {
-    delete d;
-    return Fail(KD_ERR_INVALID, "threads_per_lane must be 0, 128, 160, 192, 224, 256, 384 or 512");
-  }
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
-  if (c.search != KD_SEARCH_FASTER && c.search != KD_SEARCH_SIMPLE) {
-    delete d;
-    return Fail(KD_ERR_INVALID, "kd_decoder_config.search must be KD_SEARCH_FASTER or KD_SEARCH_SIMPLE");
-  }
   d->simple = c.search == KD_SEARCH_SIMPLE ? 1 : 0;
   d->chunk_frames = c.chunk_frames > 0 ? c.chunk_frames : 128;
 
@@ -558,7 +612,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
     d->arena_cap = c.arena_records;
   } else {
     size_t free_b = 0, total_b = 0;
-    KD_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    KD_CUDA_D(cudaMemGetInfo(&free_b, &total_b));
     double budget = 0.5 * static_cast<double>(free_b) - static_cast<double>(table_bytes_per_lane * L);
     long long per_lane = static_cast<long long>(budget / (20.0 * static_cast<double>(L)));
     d->arena_cap = std::max<long long>(1 << 16, std::min<long long>(per_lane, 1ll << 25));
@@ -571,25 +625,31 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
       (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
       (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) ||
       (rc = DevAlloc(&d->front, L * kd::kFrontCap)) || (rc = DevAlloc(&d->d_items, L)) ||
-      (rc = DevAlloc(&d->d_out_off, L)) || (rc = DevAlloc(&d->d_progress, static_cast<size_t>(1)))) {
-    kd_decoder_destroy(d);
-    return rc;
-  }
-  d->n_counters = static_cast<int32_t>(L) + 4096;
-  if ((rc = DevAlloc(&d->d_counters, static_cast<size_t>(d->n_counters)))) {
-    kd_decoder_destroy(d);
-    return rc;
-  }
+      (rc = DevAlloc(&d->d_out_off, L)) || (rc = DevAlloc(&d->d_flags, L)))
+    return fail(rc);
   d->device_bytes = L * (sizeof(kd::LaneState) + A * 20 + table_bytes_per_lane);
-  KD_CUDA(cudaMemset(d->lanes, 0, L * sizeof(kd::LaneState)));
-  KD_CUDA(cudaMemset(d->table, 0xFF, L * d->hcap * sizeof(kd::Entry)));
-  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
-  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
-
-  KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
-  for (int i = 0; i < kNumStreams; ++i) {
-    KD_CUDA(cudaStreamCreateWithFlags(&d->streams[i], cudaStreamNonBlocking));
-    KD_CUDA(cudaEventCreateWithFlags(&d->ev_stream[i], cudaEventDisableTiming));
+  KD_CUDA_D(cudaMemset(d->lanes, 0, L * sizeof(kd::LaneState)));
+  KD_CUDA_D(cudaMemset(d->table, 0xFF, L * d->hcap * sizeof(kd::Entry)));
+  KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
+  KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
+  KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
+  KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_flags), L * sizeof(int32_t)));
+  KD_CUDA_D(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  KD_CUDA_D(cudaEventCreate(&d->ev_span_begin));
+  KD_CUDA_D(cudaEventCreate(&d->ev_span_end));
+  for (int i = 0; i < kNumSlots; ++i) {
+    kd_slot &s = d->slots[i];
+    KD_CUDA_D(cudaStreamCreateWithFlags(&s.sc, cudaStreamNonBlocking));
+    KD_CUDA_D(cudaStreamCreateWithFlags(&s.sx, cudaStreamNonBlocking));
+    KD_CUDA_D(cudaEventCreateWithFlags(&s.ev_gate, cudaEventDisableTiming));
+    KD_CUDA_D(cudaEventCreateWithFlags(&s.ev_dep, cudaEventDisableTiming));
+    KD_CUDA_D(cudaEventCreate(&s.ev_begin));
+    KD_CUDA_D(cudaEventCreate(&s.ev_end));
+    if ((rc = DevAlloc(&s.d_items, L)) || (rc = DevAlloc(&s.d_words, static_cast<size_t>(4))) ||
+        (rc = DevAlloc(&s.d_out_off, L)))
+      return fail(rc);
+    KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&s.h_items), L * sizeof(kd::AdvanceItem)));
+    KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&s.h_out_off), L * sizeof(long long)));
   }
   // Optional (KD_B200_L2_PIN=1): an L2 persistence window over the graph.  Measured
   // on the 5M-arc HLG with 1024 lanes it is a loss (253 ms vs 190 ms per 1000
@@ -608,19 +668,21 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
           win <= persist ? 1.0f : static_cast<float>(static_cast<double>(persist) / win);
       attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
       attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      for (int i = 0; i < kNumStreams; ++i)
-        cudaStreamSetAttribute(d->streams[i], cudaStreamAttributeAccessPolicyWindow, &attr);
+      for (int i = 0; i < kNumSlots; ++i)
+        cudaStreamSetAttribute(d->slots[i].sc, cudaStreamAttributeAccessPolicyWindow, &attr);
       d->l2_window_bytes = win;
       d->l2_persist_bytes = persist;
     }
     cudaGetLastError();
   }
-  KD_CUDA(cudaEventCreate(&d->ev_begin));
-  KD_CUDA(cudaEventCreate(&d->ev_end));
   d->frames.assign(L, -1);
   d->status.assign(L, 0);
   d->bp_valid.assign(L, 0);
-  KD_CUDA(cudaDeviceSynchronize());
+  d->use_final.assign(L, 1);
+  d->rf_cache.assign(L, -1);
+  d->lane_slot.assign(L, -1);
+  KD_CUDA_D(cudaDeviceSynchronize());
+#undef KD_CUDA_D
   *out = d;
   return KD_OK;
 }
@@ -639,30 +701,264 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->cand);
   cudaFree(d->front);
   cudaFree(d->d_items);
-  cudaFree(d->d_progress);
-  cudaFree(d->d_counters);
   cudaFree(d->d_out_off);
-  cudaFree(d->d_stage);
+  cudaFree(d->d_flags);
   cudaFree(d->d_path);
   if (d->h_path) cudaFreeHost(d->h_path);
   if (d->h_items) cudaFreeHost(d->h_items);
-  if (d->h_progress) cudaFreeHost(d->h_progress);
   if (d->h_lanes) cudaFreeHost(d->h_lanes);
   if (d->h_out_off) cudaFreeHost(d->h_out_off);
-  for (int i = 0; i < kNumStreams; ++i) {
-    if (d->streams[i]) cudaStreamDestroy(d->streams[i]);
-    if (d->ev_stream[i]) cudaEventDestroy(d->ev_stream[i]);
+  if (d->h_flags) cudaFreeHost(d->h_flags);
+  for (int i = 0; i < kNumSlots; ++i) {
+    kd_slot &s = d->slots[i];
+    cudaFree(s.d_items);
+    cudaFree(s.d_words);
+    cudaFree(s.d_stage);
+    cudaFree(s.d_out_off);
+    if (s.h_items) cudaFreeHost(s.h_items);
+    if (s.h_progress) cudaFreeHost(s.h_progress);
+    if (s.h_res) cudaFreeHost(s.h_res);
+    if (s.h_out_off) cudaFreeHost(s.h_out_off);
+    if (s.sc) cudaStreamDestroy(s.sc);
+    if (s.sx) cudaStreamDestroy(s.sx);
+    if (s.ev_gate) cudaEventDestroy(s.ev_gate);
+    if (s.ev_dep) cudaEventDestroy(s.ev_dep);
+    if (s.ev_begin) cudaEventDestroy(s.ev_begin);
+    if (s.ev_end) cudaEventDestroy(s.ev_end);
   }
-  if (d->ev_begin) cudaEventDestroy(d->ev_begin);
-  if (d->ev_end) cudaEventDestroy(d->ev_end);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  if (d->ev_span_begin) cudaEventDestroy(d->ev_span_begin);
+  if (d->ev_span_end) cudaEventDestroy(d->ev_span_end);
+  cudaGetLastError();
   delete d;
   return KD_OK;
 }
+
+}  // extern "C"
+
+namespace {
+
+// ---------------------------------------------------------------- calls in flight
+
+// Enqueues the search kernel of slot `s` (items already on the device) and, behind it, the
+// copies that bring back the lane states and -- KD_ADVANCE_FINALIZE -- the parked paths.
+int EnqueueSearch(kd_decoder *d, kd_slot &s) {
+  const int32_t m = static_cast<int32_t>(s.lanes.size());
+  KD_CUDA(cudaMemsetAsync(s.d_words, 0, 2 * sizeof(int32_t), s.sc));  // work counter, yield flag
+  KD_CUDA(cudaEventRecord(s.ev_begin, s.sc));
+  if (d->span_armed) {
+    KD_CUDA(cudaEventRecord(d->ev_span_begin, s.sc));
+    d->span_armed = false;
+    d->span_open = true;
+  }
+  int rc = LaunchAdvance(d, s.P, m, s.threads, s.sc);
+  if (rc) return rc;
+  s.launches++;
+  KD_CUDA(cudaEventRecord(s.ev_end, s.sc));
+  if (d->span_open) {
+    KD_CUDA(cudaEventRecord(d->ev_span_end, s.sc));
+    d->span_launches++;
+  }
+  rc = FetchLaneStates(d, m, s.lanes.data(), s.sc, false);
+  if (rc) return rc;
+  if (s.flags & KD_ADVANCE_FINALIZE) {
+    // the parked paths: lane i's four arrays are 4 * path_cap consecutive words at the head
+    // of its worklist buffer.  Consecutive lane ids come back with one 2-D copy.
+    const size_t row_bytes = static_cast<size_t>(4) * s.path_cap * sizeof(int32_t);
+    const size_t lane_pitch = static_cast<size_t>(2) * d->qcap * sizeof(uint32_t);
+    bool consecutive = lane_pitch <= d->mem_pitch;
+    for (int32_t i = 1; i < m && consecutive; ++i)
+      if (s.lanes[i] != s.lanes[i - 1] + 1) consecutive = false;
+    if (consecutive) {
+      KD_CUDA(cudaMemcpy2DAsync(s.h_res, row_bytes,
+                                d->queue + static_cast<size_t>(s.lanes[0]) * 2 * d->qcap,
+                                lane_pitch, row_bytes, m, cudaMemcpyDeviceToHost, s.sc));
+    } else {
+      for (int32_t i = 0; i < m; ++i)
+        KD_CUDA(cudaMemcpyAsync(s.h_res + static_cast<size_t>(i) * 4 * s.path_cap,
+                                d->queue + static_cast<size_t>(s.lanes[i]) * 2 * d->qcap,
+                                row_bytes, cudaMemcpyDeviceToHost, s.sc));
+    }
+  }
+  return KD_OK;
+}
+
+// Completes the call in flight in slot `si`: waits for its streams, launches again if lanes
+// yielded (their rows had not been enqueued yet), refreshes the host mirrors of its lanes.
+// The outcome is kept in the slot (rc, msg) and returned.
+int CompleteSlot(kd_decoder *d, int si) {
+  kd_slot &s = d->slots[si];
+  if (!s.busy) return s.rc;
+  const int32_t m = static_cast<int32_t>(s.lanes.size());
+  auto finish = [&](int rc) {
+    // whatever happened, nothing of this call is left running
+    cudaStreamSynchronize(s.sx);
+    cudaStreamSynchronize(s.sc);
+    s.busy = false;
+    s.rc = rc;
+    s.msg = rc ? g_error : std::string();
+    for (int32_t i = 0; i < m; ++i) d->lane_slot[s.lanes[i]] = -1;
+    d->last_kernel_ms = s.kernel_ms;
+    d->last_launches = s.launches;
+    return rc;
+  };
+#define KD_CUDA_S(expr)                                                                        \
+  do {                                                                                         \
+    cudaError_t kd_e_ = (expr);                                                                \
+    if (kd_e_ != cudaSuccess)                                                                  \
+      return finish(Fail(KD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(kd_e_))); \
+  } while (0)
+  KD_CUDA_S(cudaSetDevice(d->device));
+  int stalled_rounds = 0;
+  while (true) {
+    KD_CUDA_S(cudaStreamSynchronize(s.sx));
+    KD_CUDA_S(cudaStreamSynchronize(s.sc));
+    float ms = 0.f;
+    KD_CUDA_S(cudaEventElapsedTime(&ms, s.ev_begin, s.ev_end));
+    s.kernel_ms += ms;
+    // lanes that yielded: their rows were not there (launches serialised, or pageable host
+    // memory staged by the host thread).  Every copy is enqueued by now, so one more launch
+    // finds all rows; InitDecoding has been done by the first one.
+    int32_t behind = 0, progressed = 0;
+    for (int32_t i = 0; i < m; ++i) {
+      const kd::LaneState &L = d->h_lanes[s.lanes[i]];
+      if (L.status == 0 && L.frames_decoded < s.targets[i]) ++behind;
+      if (L.frames_decoded > s.h_items[i].offset) ++progressed;
+    }
+    if (behind == 0) break;
+    if (!s.host_input || (stalled_rounds > 0 && progressed == 0) || stalled_rounds >= 4) {
+      for (int32_t i = 0; i < m; ++i) {
+        const int32_t lane = s.lanes[i];
+        d->frames[lane] = d->h_lanes[lane].frames_decoded;
+        d->status[lane] = d->h_lanes[lane].status | kd::kStatusInputStall;
+      }
+      return finish(Fail(KD_ERR_OVERFLOW, std::string("AdvanceDecoding: ") +
+                                              StatusText(kd::kStatusInputStall)));
+    }
+    ++stalled_rounds;
+    for (int32_t i = 0; i < m; ++i) s.h_items[i].flags &= ~kd::kItemInit;
+    KD_CUDA_S(cudaMemcpyAsync(s.d_items, s.h_items, sizeof(kd::AdvanceItem) * m,
+                              cudaMemcpyHostToDevice, s.sc));
+    int rc = EnqueueSearch(d, s);
+    if (rc) return finish(rc);
+  }
+  int bad = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    const int32_t lane = s.lanes[i];
+    const kd::LaneState &L = d->h_lanes[lane];
+    d->frames[lane] = L.frames_decoded;
+    d->status[lane] = L.status;
+    d->rf_cache[lane] = -1;
+    d->bp_valid[lane] = 0;  // a path parked in the candidate buffer by an earlier call is gone
+    if (L.status != 0) {
+      if (bad == 0) bad = L.status;
+    } else if (s.flags & KD_ADVANCE_FINALIZE) {
+      d->bp_valid[lane] = 1;
+      d->rf_cache[lane] = static_cast<int8_t>(L.bp_final != 0);
+    }
+  }
+  if (bad) return finish(Fail(KD_ERR_OVERFLOW, std::string("AdvanceDecoding: ") + StatusText(bad)));
+  if (s.flags & KD_ADVANCE_FINALIZE) {
+    // word offsets of every lane's arrays in h_res; paths that could not be parked (longer
+    // than path_cap) are written by kd_best_fill_kernel into a spill area behind the block
+    s.res_off.assign(static_cast<size_t>(4) * m, 0);
+    std::vector<int32_t> spill;
+    int64_t spill_words = 0;
+    const int64_t block = static_cast<int64_t>(4) * s.path_cap;
+    for (int32_t i = 0; i < m; ++i) {
+      const kd::LaneState &L = d->h_lanes[s.lanes[i]];
+      for (int k = 0; k < 4; ++k) s.res_off[4 * i + k] = i * block + k * s.path_cap;
+      if (L.bp_ok && !L.bp_parked) {
+        spill.push_back(i);
+        spill_words += 4 * L.bp_len;
+      }
+    }
+    if (!spill.empty()) {
+      const size_t need = static_cast<size_t>(m) * block + static_cast<size_t>(spill_words);
+      if (need > s.res_words) {
+        int32_t *bigger = nullptr;
+        KD_CUDA_S(cudaMallocHost(reinterpret_cast<void **>(&bigger), need * sizeof(int32_t)));
+        memcpy(bigger, s.h_res, static_cast<size_t>(m) * block * sizeof(int32_t));
+        cudaFreeHost(s.h_res);
+        s.h_res = bigger;
+        s.res_words = need;
+      }
+      int32_t *d_spill = nullptr;
+      KD_CUDA_S(cudaMalloc(reinterpret_cast<void **>(&d_spill), spill_words * sizeof(int32_t)));
+      int64_t pos = 0;
+      const int32_t ns = static_cast<int32_t>(spill.size());
+      for (int32_t k = 0; k < ns; ++k) {
+        const int32_t i = spill[k];
+        const int64_t len = d->h_lanes[s.lanes[i]].bp_len;
+        s.h_items[k] = s.h_items[i];  // (items are spent: reused as the lane list)
+        s.h_items[k].lane = s.lanes[i];
+        s.h_out_off[k] = 0;
+        // one lane at a time: four arrays of `len` words each
+        for (int a = 0; a < 4; ++a) s.res_off[4 * i + a] = m * block + pos + a * len;
+        pos += 4 * len;
+      }
+      kd::Params P = s.P;
+      pos = 0;
+      for (int32_t k = 0; k < ns; ++k) {
+        const int64_t len = d->h_lanes[s.h_items[k].lane].bp_len;
+        KD_CUDA_S(cudaMemcpyAsync(s.d_items, s.h_items + k, sizeof(kd::AdvanceItem),
+                                  cudaMemcpyHostToDevice, s.sc));
+        KD_CUDA_S(cudaMemsetAsync(s.d_out_off, 0, sizeof(long long), s.sc));
+        P.items = s.d_items;
+        P.n_items = 1;
+        int32_t *base = d_spill + pos;
+        kd::kd_best_fill_kernel<<<1, 128, 0, s.sc>>>(P, s.d_out_off, base, base + len,
+                                                     reinterpret_cast<float *>(base + 2 * len),
+                                                     reinterpret_cast<float *>(base + 3 * len));
+        KD_CUDA_S(cudaStreamSynchronize(s.sc));
+        pos += 4 * len;
+      }
+      KD_CUDA_S(cudaMemcpy(s.h_res + static_cast<size_t>(m) * block, d_spill,
+                           spill_words * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      cudaFree(d_spill);
+    }
+    s.res_valid = true;
+  }
+#undef KD_CUDA_S
+  return finish(KD_OK);
+}
+
+// Deferred synchronisation: whoever touches a lane first completes the call that owns it.
+int WaitLanes(kd_decoder *d, int32_t n, const int32_t *lanes) {
+  int rc = KD_OK;
+  for (int32_t i = 0; i < n; ++i) {
+    const int si = d->lane_slot[lanes[i]];
+    if (si >= 0) {
+      const int r = CompleteSlot(d, si);
+      if (r && !rc) rc = r;
+    }
+  }
+  return rc;
+}
+
+int WaitAll(kd_decoder *d) {
+  int rc = KD_OK;
+  // oldest first
+  for (int round = 0; round < kNumSlots; ++round) {
+    int best = -1;
+    for (int i = 0; i < kNumSlots; ++i)
+      if (d->slots[i].busy && (best < 0 || d->slots[i].ticket < d->slots[best].ticket)) best = i;
+    if (best < 0) break;
+    const int r = CompleteSlot(d, best);
+    if (r && !rc) rc = r;
+  }
+  return rc;
+}
+
+}  // namespace
+
+extern "C" {
 
 int kd_decoder_set_options(kd_decoder *d, const kd_options *opts) {
   if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
   int rc = CheckOptions(opts);
   if (rc) return rc;
+  WaitAll(d);  // calls in flight keep the options they were enqueued with
   d->opts = *opts;
   return KD_OK;
 }
@@ -672,7 +968,8 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
   if (rc) return rc;
   if (n == 0) return KD_OK;
   KD_CUDA(cudaSetDevice(d->device));
-  cudaStream_t s = d->streams[0];
+  WaitLanes(d, n, lanes);  // (a failed call on these lanes is wiped out by this init)
+  cudaStream_t s = d->stream;
   for (int32_t i = 0; i < n; ++i) {
     const int32_t lane = lanes[i];
     if (d->status[lane] != 0) {
@@ -681,25 +978,23 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
       KD_CUDA(cudaMemsetAsync(d->table + off, 0xFF, d->hcap * sizeof(kd::Entry), s));
       d->status[lane] = 0;
     }
+    memset(&d->h_items[i], 0, sizeof(kd::AdvanceItem));
     d->h_items[i].lane = lane;
-    d->h_items[i].rows = 0;
-    d->h_items[i].offset = 0;
-    d->h_items[i].target = 0;
-    d->h_items[i].logp = nullptr;
   }
   KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
                           cudaMemcpyHostToDevice, s));
   kd::Params P = MakeParams(d);
+  P.items = d->d_items;
   P.n_items = n;
   kd::kd_init_kernel<256><<<n, 256, 0, s>>>(P);
   KD_CUDA(cudaGetLastError());
-  KD_CUDA(cudaStreamSynchronize(s));
-  rc = FetchLaneStates(d, n, lanes);
+  rc = FetchLaneStates(d, n, lanes, s);
   if (rc) return rc;
   for (int32_t i = 0; i < n; ++i) {
     const int32_t lane = lanes[i];
     d->frames[lane] = 0;
     d->bp_valid[lane] = 0;
+    d->rf_cache[lane] = -1;
     d->status[lane] = d->h_lanes[lane].status;
     if (d->status[lane] != 0)
       return Fail(KD_ERR_OVERFLOW, std::string("InitDecoding: ") + StatusText(d->status[lane]));
@@ -707,39 +1002,44 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
   return KD_OK;
 }
 
-int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
-                       const float *const *logprobs, const int32_t *rows, int32_t cols,
-                       const int32_t *offsets, int32_t max_num_frames, int mem_kind) {
+int kd_decoder_advance_async(kd_decoder *d, int32_t n, const int32_t *lanes,
+                             const float *const *logprobs, const int32_t *rows, int32_t cols,
+                             const int32_t *offsets, int32_t max_num_frames, int mem_kind,
+                             int flags, void *producer_stream, int64_t *ticket) {
+  if (ticket) *ticket = -1;
   int rc = CheckLanes(d, n, lanes);
   if (rc) return rc;
   if (n == 0) return KD_OK;
   if (!logprobs || !rows) return Fail(KD_ERR_INVALID, "null logprobs/rows");
   if (mem_kind != KD_MEM_HOST && mem_kind != KD_MEM_DEVICE)
     return Fail(KD_ERR_INVALID, "bad mem_kind");
+  if (flags & ~(KD_ADVANCE_INIT | KD_ADVANCE_FINALIZE)) return Fail(KD_ERR_INVALID, "bad flags");
   if (cols < d->g->max_ilabel)
     return Fail(KD_ERR_INVALID,
                 "decodable has fewer columns than the largest ilabel of the graph "
                 "(the reference would read out of bounds, decodable-ctc.cc:28)");
   KD_CUDA(cudaSetDevice(d->device));
-  d->last_kernel_ms = 0.f;
-  d->last_launches = 0;
+  // a lane is owned by one call at a time: calls in flight on these lanes complete first
+  rc = WaitLanes(d, n, lanes);
+  if (rc && !(flags & KD_ADVANCE_INIT)) return rc;
 
   // per-lane targets (faster-decoder.cc:128-144)
   struct Work {
-    int32_t lane, target, first_row, n_rows;
+    int32_t lane, decoded, target, n_rows;
     const float *src;
   };
   std::vector<Work> work;
   work.reserve(n);
   size_t stage_need = 0;
+  int32_t max_rows = 0;
   for (int32_t i = 0; i < n; ++i) {
     const int32_t lane = lanes[i];
-    const int32_t decoded = d->frames[lane];
+    const int32_t decoded = (flags & KD_ADVANCE_INIT) ? 0 : d->frames[lane];
     if (decoded < 0)
       return Fail(KD_ERR_INVALID,
                   "Check failed!\nx: num_frames_decoded_ >= 0 && \"You must call "
                   "InitDecoding() before AdvanceDecoding()\"");
-    if (d->status[lane] != 0)
+    if (d->status[lane] != 0 && !(flags & KD_ADVANCE_INIT))
       return Fail(KD_ERR_OVERFLOW, std::string("lane is in error state: ") +
                                        StatusText(d->status[lane]));
     if (rows[i] < 0) return Fail(KD_ERR_INVALID, "negative rows");
@@ -749,73 +1049,141 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       return Fail(KD_ERR_INVALID, "Check failed!\nx: num_frames_ready >= num_frames_decoded_");
     int32_t target = ready;
     if (max_num_frames >= 0) target = std::min(target, decoded + max_num_frames);
-    if (target <= decoded) continue;
-    if (decoded < off)
-      return Fail(KD_ERR_INVALID, "decodable offset is beyond the frames decoded so far");
-    if (!logprobs[i]) return Fail(KD_ERR_INVALID, "null log-prob matrix");
+    // (a lane with nothing to decode still takes part when it is to be initialised or finalized)
+    if (target <= decoded && flags == 0) continue;
+    if (target < decoded) target = decoded;
+    if (target > decoded) {
+      if (decoded < off)
+        return Fail(KD_ERR_INVALID, "decodable offset is beyond the frames decoded so far");
+      if (!logprobs[i]) return Fail(KD_ERR_INVALID, "null log-prob matrix");
+    }
     Work w;
     w.lane = lane;
+    w.decoded = decoded;
     w.target = target;
-    w.first_row = decoded - off;
     w.n_rows = target - decoded;
-    w.src = logprobs[i] + static_cast<size_t>(w.first_row) * cols;
+    w.src = w.n_rows > 0 ? logprobs[i] + static_cast<size_t>(decoded - off) * cols : nullptr;
     work.push_back(w);
     stage_need += static_cast<size_t>(w.n_rows) * cols;
+    max_rows = std::max(max_rows, w.n_rows);
   }
   if (work.empty()) return KD_OK;
   const int32_t m = static_cast<int32_t>(work.size());
 
+  // a free slot; if all are in flight the oldest completes first
+  int si = -1;
+  for (int i = 0; i < kNumSlots; ++i)
+    if (!d->slots[i].busy && (si < 0 || d->slots[i].ticket < d->slots[si].ticket)) si = i;
+  if (si < 0) {
+    for (int i = 0; i < kNumSlots; ++i)
+      if (si < 0 || d->slots[i].ticket < d->slots[si].ticket) si = i;
+    CompleteSlot(d, si);  // its outcome stays in the slot for kd_decoder_wait
+  }
+  kd_slot &s = d->slots[si];
+  s.res_valid = false;
+  s.kernel_ms = 0.f;
+  s.launches = 0;
+  s.flags = flags;
+  s.host_input = mem_kind == KD_MEM_HOST;
+  s.lanes.resize(m);
+  s.targets.resize(m);
+  s.path_cap = 0;
+  if (flags & KD_ADVANCE_FINALIZE) {
+    // room for the path of the longest lane: its frames so far plus half as many epsilon
+    // arcs (a longer path is fetched through kd_best_fill_kernel instead)
+    int32_t longest = 0;
+    for (int32_t i = 0; i < m; ++i) longest = std::max(longest, work[i].target);
+    int64_t cap = (static_cast<int64_t>(longest) * 3 / 2 + 64 + 31) / 32 * 32;
+    cap = std::min<int64_t>(cap, d->qcap / 2);
+    s.path_cap = static_cast<int32_t>(cap);
+    const size_t need = static_cast<size_t>(m) * 4 * s.path_cap;
+    if (need > s.res_words) {
+      if (s.h_res) cudaFreeHost(s.h_res);
+      s.h_res = nullptr;
+      s.res_words = 0;
+      KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&s.h_res), need * sizeof(int32_t)));
+      s.res_words = need;
+    }
+  }
+
   kd::Params P = MakeParams(d);
   P.cols = cols;
   P.row_in_smem = (static_cast<size_t>(cols) * 6 <= 49152) ? 1 : 0;
+  P.items = s.d_items;
+  P.n_items = m;
+  P.work_counter = s.d_words;
+  P.yield_flag = s.d_words + 1;
+  P.progress = nullptr;
+  s.threads = PickThreads(d, m);
 
-  if (mem_kind == KD_MEM_DEVICE) {
-    for (int32_t i = 0; i < m; ++i) {
-      d->h_items[i].lane = work[i].lane;
-      d->h_items[i].rows = work[i].n_rows;
-      d->h_items[i].offset = d->frames[work[i].lane];
-      d->h_items[i].target = work[i].target;
-      d->h_items[i].logp = work[i].src;
-    }
-    cudaStream_t s = d->streams[0];
-    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
-                            cudaMemcpyHostToDevice, s));
-    KD_CUDA(cudaMemsetAsync(d->d_counters, 0, sizeof(int32_t), s));
-    P.n_items = m;
-    P.work_counter = d->d_counters;
-    KD_CUDA(cudaEventRecord(d->ev_begin, s));
-    rc = LaunchAdvance(d, P, m, PickThreads(d, m), s);
+  if (s.host_input && stage_need > s.stage_floats) {
+    // (cudaFree waits for the device: growth is rare and only happens while ramping up)
+    cudaFree(s.d_stage);
+    s.d_stage = nullptr;
+    s.stage_floats = 0;
+    rc = DevAlloc(&s.d_stage, stage_need);
     if (rc) return rc;
-    KD_CUDA(cudaEventRecord(d->ev_end, s));
-    KD_CUDA(cudaStreamSynchronize(s));
-  } else {
-    // Host matrices: ONE search launch; the copy stream delivers the frames in time
-    // chunks (all lanes, `chunk_frames` frames each) and publishes its progress in a
-    // device word the lanes poll when they run out of rows.  Lanes are latency bound
-    // and independent, so every lane should start as soon as its first frames are
-    // there and never wait for other lanes (relaunching per chunk costs the
-    // slowest-lane tail once per chunk: measured 189 vs 170 ms per step).
-    if (stage_need > d->stage_floats) {
-      KD_CUDA(cudaDeviceSynchronize());
-      cudaFree(d->d_stage);
-      d->d_stage = nullptr;
-      d->stage_floats = 0;
-      rc = DevAlloc(&d->d_stage, stage_need);
-      if (rc) return rc;
-      d->stage_floats = stage_need;
-    }
-    const int32_t F = d->chunk_frames;
-    int32_t max_rows = 0;
-    size_t pos = 0;
-    for (int32_t i = 0; i < m; ++i) {
-      max_rows = std::max(max_rows, work[i].n_rows);
-      d->h_items[i].lane = work[i].lane;
-      d->h_items[i].rows = work[i].n_rows;
-      d->h_items[i].offset = d->frames[work[i].lane];
-      d->h_items[i].target = work[i].target;
-      d->h_items[i].logp = d->d_stage + pos;
+    s.stage_floats = stage_need;
+  }
+  size_t pos = 0;
+  for (int32_t i = 0; i < m; ++i) {
+    const int32_t lane = work[i].lane;
+    s.lanes[i] = lane;
+    s.targets[i] = work[i].target;
+    kd::AdvanceItem &it = s.h_items[i];
+    it.lane = lane;
+    it.rows = work[i].n_rows;
+    it.offset = work[i].decoded;
+    it.target = work[i].target;
+    it.flags = flags;
+    it.path_cap = s.path_cap;
+    if (s.host_input) {
+      it.logp = s.d_stage + pos;
       pos += static_cast<size_t>(work[i].n_rows) * cols;
+    } else {
+      it.logp = work[i].src;
     }
+    if ((flags & KD_ADVANCE_INIT) && d->status[lane] != 0) {
+      // a lane that overflowed may have left claimed table slots behind
+      KD_CUDA(cudaMemsetAsync(d->table + static_cast<size_t>(lane) * d->hcap, 0xFF,
+                              d->hcap * sizeof(kd::Entry), s.sc));
+      d->status[lane] = 0;
+    }
+  }
+  KD_CUDA(cudaMemcpyAsync(s.d_items, s.h_items, sizeof(kd::AdvanceItem) * m,
+                          cudaMemcpyHostToDevice, s.sc));
+
+  // From here on work is enqueued: the slot is in flight, and a failure completes it.
+  s.busy = true;
+  s.ticket = d->next_ticket++;
+  s.rc = KD_OK;
+  s.P = P;
+  for (int32_t i = 0; i < m; ++i) {
+    d->lane_slot[s.lanes[i]] = static_cast<int8_t>(si);
+    d->bp_valid[s.lanes[i]] = 0;
+    d->rf_cache[s.lanes[i]] = -1;
+    if (flags & KD_ADVANCE_INIT) d->frames[s.lanes[i]] = 0;
+  }
+  auto enqueue = [&]() -> int {
+    if (!s.host_input) {
+      // Device matrices: the search must not start before the work that produces them.
+      // `producer_stream` is the stream that work was enqueued on (NULL: the legacy default
+      // stream, which also orders behind every blocking stream).
+      cudaStream_t ps = producer_stream ? static_cast<cudaStream_t>(producer_stream)
+                                        : cudaStreamLegacy;
+      KD_CUDA(cudaEventRecord(s.ev_dep, ps));
+      KD_CUDA(cudaStreamWaitEvent(s.sc, s.ev_dep, 0));
+      return EnqueueSearch(d, s);
+    }
+    // Host matrices: ONE search launch; the copy stream delivers the frames in time chunks
+    // (all lanes, `chunk_frames` frames each) and publishes its progress in a device word
+    // the lanes poll when they run out of rows.  Lanes are latency bound and independent,
+    // so every lane starts as soon as its first frames are there and never waits for other
+    // lanes (relaunching per chunk costs the slowest-lane tail once per chunk: measured
+    // 189 vs 170 ms per step).  The copies are enqueued BEFORE the search kernel: under
+    // serialised launches (CUDA_LAUNCH_BLOCKING, profilers) a kernel launched first would
+    // poll for rows nobody can enqueue any more.
+    const int32_t F = d->chunk_frames;
     // Chunk ends: the first chunks are small (F/16, F/8, ... frames) so the lanes start
     // after a fraction of a millisecond instead of one full chunk's copy time; the copy
     // engine delivers frames about twice as fast as the lanes consume them, so it stays
@@ -827,91 +1195,172 @@ int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
       step = std::min(F, step * 2);
     }
     const int32_t n_chunks = static_cast<int32_t>(ends.size());
-    if (n_chunks > d->progress_cap) {
-      KD_CUDA(cudaDeviceSynchronize());
-      if (d->h_progress) cudaFreeHost(d->h_progress);
-      d->h_progress = nullptr;
-      d->progress_cap = 0;
-      KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_progress),
+    if (n_chunks > s.progress_cap) {
+      if (s.h_progress) cudaFreeHost(s.h_progress);
+      s.h_progress = nullptr;
+      s.progress_cap = 0;
+      KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&s.h_progress),
                              sizeof(int32_t) * (static_cast<size_t>(n_chunks) + 64)));
-      d->progress_cap = n_chunks + 64;
+      s.progress_cap = n_chunks + 64;
     }
     // one 2-D copy per chunk when the host matrices are equally long and equally spaced
+    // (and the spacing is a pitch the copy engine takes)
     bool uniform = m > 1;
     ptrdiff_t src_stride = 0;
     if (uniform) {
       src_stride = work[1].src - work[0].src;
-      if (src_stride < static_cast<ptrdiff_t>(static_cast<size_t>(work[0].n_rows) * cols))
-        uniform = false;  // overlapping, unordered or identical matrices
+      if (src_stride < static_cast<ptrdiff_t>(static_cast<size_t>(work[0].n_rows) * cols) ||
+          static_cast<size_t>(src_stride) * sizeof(float) > d->mem_pitch ||
+          static_cast<size_t>(work[0].n_rows) * cols * sizeof(float) > d->mem_pitch)
+        uniform = false;  // overlapping, unordered, identical or too far apart
       for (int32_t i = 1; i < m && uniform; ++i) {
         if (work[i].n_rows != work[0].n_rows) uniform = false;
         if (work[i].src - work[i - 1].src != src_stride) uniform = false;
       }
     }
-    cudaStream_t sc = d->streams[0], sx = d->streams[1];  // search, copy
-    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * m,
-                            cudaMemcpyHostToDevice, sc));
-    KD_CUDA(cudaMemsetAsync(d->d_counters, 0, sizeof(int32_t), sc));
-    KD_CUDA(cudaMemsetAsync(d->d_progress, 0, sizeof(int32_t), sc));
-    KD_CUDA(cudaEventRecord(d->ev_begin, sc));
-    KD_CUDA(cudaStreamWaitEvent(sx, d->ev_begin, 0));  // copies start after the progress reset
-    P.n_items = m;
-    P.work_counter = d->d_counters;
-    P.progress = d->d_progress;
-    rc = LaunchAdvance(d, P, m, PickThreads(d, m), sc);
-    if (rc) return rc;
-    KD_CUDA(cudaEventRecord(d->ev_end, sc));
+    KD_CUDA(cudaMemsetAsync(s.d_words + 2, 0, sizeof(int32_t), s.sc));
+    KD_CUDA(cudaEventRecord(s.ev_gate, s.sc));
+    KD_CUDA(cudaStreamWaitEvent(s.sx, s.ev_gate, 0));  // copies start after the progress reset
+    s.P.progress = s.d_words + 2;
+    // Per-lane copies (matrices of different lengths or spacing) cost ~3 us of host time
+    // each: only the first ~2000 go out before the launch, the rest behind it; should the
+    // launch turn out to be blocking, lanes that run dry yield and are launched again.
+    int64_t copies_before_launch = (uniform || d->launch_blocking) ? (1ll << 60) : 2048;
+    // (test knob: launch after this many copies whatever the layout -- with serialised
+    // launches this exercises the yield-and-launch-again path)
+    if (const char *e = getenv("KD_B200_COPIES_BEFORE_LAUNCH")) {
+      copies_before_launch = atoll(e);
+      if (uniform && copies_before_launch <= 0) copies_before_launch = 1;
+    }
+    bool launched = false;
     for (int32_t c = 0; c < n_chunks; ++c) {
       const int32_t r0 = c == 0 ? 0 : ends[c - 1];
       const int32_t Fc = ends[c] - r0;  // frames of this chunk
       if (uniform) {
         const int32_t rows_c = std::min(Fc, work[0].n_rows - r0);
         const size_t lane_floats = static_cast<size_t>(work[0].n_rows) * cols;
-        KD_CUDA(cudaMemcpy2DAsync(d->d_stage + static_cast<size_t>(r0) * cols,
+        KD_CUDA(cudaMemcpy2DAsync(s.d_stage + static_cast<size_t>(r0) * cols,
                                   lane_floats * sizeof(float),
                                   work[0].src + static_cast<size_t>(r0) * cols,
                                   static_cast<size_t>(src_stride) * sizeof(float),
                                   static_cast<size_t>(rows_c) * cols * sizeof(float), m,
-                                  cudaMemcpyHostToDevice, sx));
+                                  cudaMemcpyHostToDevice, s.sx));
+        --copies_before_launch;
       } else {
         for (int32_t i = 0; i < m; ++i) {
           if (r0 >= work[i].n_rows) continue;
           const int32_t rows_c = std::min(Fc, work[i].n_rows - r0);
           KD_CUDA(cudaMemcpyAsync(
-              const_cast<float *>(d->h_items[i].logp) + static_cast<size_t>(r0) * cols,
+              const_cast<float *>(s.h_items[i].logp) + static_cast<size_t>(r0) * cols,
               work[i].src + static_cast<size_t>(r0) * cols,
-              sizeof(float) * static_cast<size_t>(rows_c) * cols, cudaMemcpyHostToDevice, sx));
+              sizeof(float) * static_cast<size_t>(rows_c) * cols, cudaMemcpyHostToDevice, s.sx));
+          --copies_before_launch;
         }
       }
-      d->h_progress[c] = ends[c];
-      KD_CUDA(cudaMemcpyAsync(d->d_progress, d->h_progress + c, sizeof(int32_t),
-                              cudaMemcpyHostToDevice, sx));
+      s.h_progress[c] = ends[c];
+      KD_CUDA(cudaMemcpyAsync(s.d_words + 2, s.h_progress + c, sizeof(int32_t),
+                              cudaMemcpyHostToDevice, s.sx));
+      if (!launched && copies_before_launch <= 0) {
+        const int r = EnqueueSearch(d, s);
+        if (r) return r;
+        launched = true;
+      }
     }
-    KD_CUDA(cudaStreamSynchronize(sx));
-    KD_CUDA(cudaStreamSynchronize(sc));
+    if (!launched) return EnqueueSearch(d, s);
+    return KD_OK;
+  };
+  rc = enqueue();
+  if (rc) {
+    // nothing of a failed call keeps running; its lanes are unusable until InitDecoding
+    const std::string keep = g_error;
+    cudaStreamSynchronize(s.sx);
+    cudaStreamSynchronize(s.sc);
+    for (int32_t i = 0; i < m; ++i) {
+      d->lane_slot[s.lanes[i]] = -1;
+      d->status[s.lanes[i]] |= kd::kStatusInputStall;
+    }
+    s.busy = false;
+    s.rc = rc;
+    s.msg = keep;
+    g_error = keep;
+    return rc;
   }
-  KD_CUDA(cudaEventElapsedTime(&d->last_kernel_ms, d->ev_begin, d->ev_end));
+  if (ticket) *ticket = s.ticket;
+  return KD_OK;
+}
 
-  // status + frame counters
-  std::vector<int32_t> used(m);
-  for (int32_t i = 0; i < m; ++i) used[i] = work[i].lane;
-  rc = FetchLaneStates(d, m, used.data());
-  if (rc) return rc;
-  int bad = 0;
-  for (int32_t i = 0; i < m; ++i) {
-    const int32_t lane = work[i].lane;
-    d->frames[lane] = d->h_lanes[lane].frames_decoded;
-    d->bp_valid[lane] = 0;  // the path parked in the candidate buffer is gone
-    d->status[lane] = d->h_lanes[lane].status;
-    if (d->status[lane] != 0 && bad == 0) bad = d->status[lane];
+int kd_decoder_wait(kd_decoder *d, int64_t ticket) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  if (ticket < 0) return WaitAll(d);
+  for (int i = 0; i < kNumSlots; ++i) {
+    kd_slot &s = d->slots[i];
+    if (s.ticket != ticket) continue;
+    if (s.busy) return CompleteSlot(d, i);
+    if (s.rc) g_error = s.msg;  // completed by a later call on its lanes
+    return s.rc;
   }
-  if (bad) return Fail(KD_ERR_OVERFLOW, std::string("AdvanceDecoding: ") + StatusText(bad));
+  return KD_OK;  // long done: its slot has been reused
+}
+
+int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
+                       const float *const *logprobs, const int32_t *rows, int32_t cols,
+                       const int32_t *offsets, int32_t max_num_frames, int mem_kind) {
+  int64_t ticket = -1;
+  int rc = kd_decoder_advance_async(d, n, lanes, logprobs, rows, cols, offsets, max_num_frames,
+                                    mem_kind, 0, nullptr, &ticket);
+  if (rc || ticket < 0) return rc;
+  return kd_decoder_wait(d, ticket);
+}
+
+int kd_decoder_result_view(kd_decoder *d, int64_t ticket, int use_final_probs,
+                           int32_t *num_lanes, const int32_t **lanes, const int32_t **words,
+                           const int64_t **word_offsets, int64_t *num_arcs, int32_t *ok,
+                           int32_t *reached_final, float *final_weight2) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  int si = -1;
+  for (int i = 0; i < kNumSlots; ++i)
+    if (d->slots[i].ticket == ticket) si = i;
+  if (si < 0 || ticket < 0)
+    return Fail(KD_ERR_INVALID, "unknown ticket (its slot has been reused by a later call)");
+  kd_slot &s = d->slots[si];
+  if (s.busy) {
+    int rc = CompleteSlot(d, si);
+    if (rc) return rc;
+  }
+  if (s.rc) {
+    g_error = s.msg;
+    return s.rc;
+  }
+  if (!(s.flags & KD_ADVANCE_FINALIZE) || !s.res_valid)
+    return Fail(KD_ERR_INVALID, "the call was not made with KD_ADVANCE_FINALIZE");
+  const int32_t m = static_cast<int32_t>(s.lanes.size());
+  if (num_lanes) *num_lanes = m;
+  if (lanes) *lanes = s.lanes.data();
+  if (words) *words = s.h_res;
+  if (word_offsets) *word_offsets = s.res_off.data();
+  for (int32_t i = 0; i < m; ++i) {
+    const int32_t lane = s.lanes[i];
+    if (d->lane_slot[lane] >= 0 || !d->bp_valid[lane])
+      return Fail(KD_ERR_INVALID, "a lane of this call has been advanced or initialised since");
+    const kd::LaneState &L = d->h_lanes[lane];
+    d->use_final[lane] = use_final_probs ? 1 : 0;
+    if (ok) ok[i] = L.bp_ok;
+    if (reached_final) reached_final[i] = L.bp_final;
+    if (num_arcs) num_arcs[i] = L.bp_ok ? L.bp_len : 0;
+    if (final_weight2) {
+      // faster-decoder.cc:416-421
+      const bool fin = L.bp_ok && L.bp_final && use_final_probs;
+      final_weight2[2 * i] = fin ? L.bp_final_w : 0.f;
+      final_weight2[2 * i + 1] = 0.f;
+    }
+  }
   return KD_OK;
 }
 
 int kd_decoder_num_frames_decoded(kd_decoder *d, int32_t lane, int32_t *out) {
   int rc = CheckLanes(d, 1, &lane);
   if (rc) return rc;
+  WaitLanes(d, 1, &lane);
   if (out) *out = d->frames[lane];
   return KD_OK;
 }
@@ -923,27 +1372,36 @@ int kd_decoder_best_path_prepare(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (rc) return rc;
   if (n == 0) return KD_OK;
   KD_CUDA(cudaSetDevice(d->device));
+  rc = WaitLanes(d, n, lanes);
+  if (rc) return rc;
+  // lanes whose last search launch already selected their path (KD_ADVANCE_FINALIZE) are done
+  int32_t todo = 0;
   for (int32_t i = 0; i < n; ++i) {
     if (d->frames[lanes[i]] < 0)
       return Fail(KD_ERR_INVALID, "lane not initialised (call InitDecoding first)");
-    d->h_items[i].lane = lanes[i];
-    d->h_items[i].rows = d->h_items[i].offset = d->h_items[i].target = 0;
-    d->h_items[i].logp = nullptr;
+    if (d->bp_valid[lanes[i]]) continue;
+    memset(&d->h_items[todo], 0, sizeof(kd::AdvanceItem));
+    d->h_items[todo].lane = lanes[i];
+    ++todo;
   }
-  cudaStream_t s = d->streams[0];
-  KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
-                          cudaMemcpyHostToDevice, s));
-  kd::Params P = MakeParams(d);
-  P.n_items = n;
-  kd::kd_best_select_kernel<256><<<n, 256, 0, s>>>(P);
-  KD_CUDA(cudaGetLastError());
-  KD_CUDA(cudaStreamSynchronize(s));
-  rc = FetchLaneStates(d, n, lanes);
-  if (rc) return rc;
-  d->last_use_final = use_final_probs ? 1 : 0;
+  if (todo > 0) {
+    cudaStream_t s = d->stream;
+    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * todo,
+                            cudaMemcpyHostToDevice, s));
+    kd::Params P = MakeParams(d);
+    P.items = d->d_items;
+    P.n_items = todo;
+    kd::kd_best_select_kernel<256><<<todo, 256, 0, s>>>(P);
+    KD_CUDA(cudaGetLastError());
+    rc = FetchLaneStates(d, n, lanes, s);
+    if (rc) return rc;
+  }
   for (int32_t i = 0; i < n; ++i) {
-    d->bp_valid[lanes[i]] = 1;
-    const kd::LaneState &L = d->h_lanes[lanes[i]];
+    const int32_t lane = lanes[i];
+    d->bp_valid[lane] = 1;
+    d->use_final[lane] = use_final_probs ? 1 : 0;
+    const kd::LaneState &L = d->h_lanes[lane];
+    d->rf_cache[lane] = static_cast<int8_t>(L.bp_final != 0);
     if (ok) ok[i] = L.bp_ok;
     if (reached_final) reached_final[i] = L.bp_final;
     if (num_arcs) num_arcs[i] = L.bp_ok ? L.bp_len : 0;
@@ -965,6 +1423,8 @@ int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (n == 0) return KD_OK;
   if (!out_offsets || total_arcs < 0) return Fail(KD_ERR_INVALID, "bad output layout");
   KD_CUDA(cudaSetDevice(d->device));
+  rc = WaitLanes(d, n, lanes);
+  if (rc) return rc;
   for (int32_t i = 0; i < n; ++i) {
     if (!d->bp_valid[lanes[i]])
       return Fail(KD_ERR_INVALID,
@@ -973,18 +1433,19 @@ int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
     const kd::LaneState &L = d->h_lanes[lanes[i]];
     if (L.bp_ok && (out_offsets[i] < 0 || out_offsets[i] + L.bp_len > total_arcs))
       return Fail(KD_ERR_INVALID, "best path does not fit the output arrays");
+    memset(&d->h_items[i], 0, sizeof(kd::AdvanceItem));
     d->h_items[i].lane = lanes[i];
     d->h_out_off[i] = out_offsets[i];
     if (final_weight2) {
       // faster-decoder.cc:416-421
-      const bool fin = L.bp_ok && L.bp_final && d->last_use_final;
+      const bool fin = L.bp_ok && L.bp_final && d->use_final[lanes[i]];
       final_weight2[2 * i] = fin ? L.bp_final_w : 0.f;
       final_weight2[2 * i + 1] = 0.f;
     }
   }
   if (total_arcs == 0) return KD_OK;
   if (total_arcs > d->path_cap) {
-    KD_CUDA(cudaDeviceSynchronize());
+    KD_CUDA(cudaStreamSynchronize(d->stream));
     cudaFree(d->d_path);
     if (d->h_path) cudaFreeHost(d->h_path);
     d->d_path = d->h_path = nullptr;
@@ -994,12 +1455,13 @@ int kd_decoder_best_path_view(kd_decoder *d, int32_t n, const int32_t *lanes,
     KD_CUDA(cudaMallocHost(reinterpret_cast<void **>(&d->h_path), 4 * cap * sizeof(int32_t)));
     d->path_cap = static_cast<int64_t>(cap);
   }
-  cudaStream_t s = d->streams[0];
+  cudaStream_t s = d->stream;
   KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem) * n,
                           cudaMemcpyHostToDevice, s));
   KD_CUDA(cudaMemcpyAsync(d->d_out_off, d->h_out_off, sizeof(long long) * n,
                           cudaMemcpyHostToDevice, s));
   kd::Params P = MakeParams(d);
+  P.items = d->d_items;
   P.n_items = n;
   // the four arrays are packed total_arcs apart: one contiguous copy brings them back
   const size_t nb = static_cast<size_t>(total_arcs);
@@ -1056,7 +1518,10 @@ int kd_decoder_best_path(kd_decoder *d, int32_t lane, int use_final_probs, int64
 int kd_decoder_final_relative_cost(kd_decoder *d, int32_t lane, float *out) {
   int32_t okv = 0, rf = 0;
   int64_t len = 0;
-  int rc = kd_decoder_best_path_prepare(d, 1, &lane, 1, &okv, &rf, &len);
+  int rc = CheckLanes(d, 1, &lane);
+  if (rc) return rc;
+  // (the selection does not depend on use_final_probs: the lane keeps its own setting)
+  rc = kd_decoder_best_path_prepare(d, 1, &lane, d->use_final[lane], &okv, &rf, &len);
   if (rc) return rc;
   const kd::LaneState &L = d->h_lanes[lane];
   float v = std::numeric_limits<float>::infinity();
@@ -1068,11 +1533,31 @@ int kd_decoder_final_relative_cost(kd_decoder *d, int32_t lane, float *out) {
 }
 
 int kd_decoder_reached_final(kd_decoder *d, int32_t lane, int32_t *out) {
-  int32_t okv = 0, rf = 0;
-  int64_t len = 0;
-  int rc = kd_decoder_best_path_prepare(d, 1, &lane, d ? d->last_use_final : 1, &okv, &rf, &len);
+  int rc = CheckLanes(d, 1, &lane);
   if (rc) return rc;
-  if (out) *out = rf;
+  KD_CUDA(cudaSetDevice(d->device));
+  rc = WaitLanes(d, 1, &lane);
+  if (rc) return rc;
+  if (d->frames[lane] < 0)
+    return Fail(KD_ERR_INVALID, "lane not initialised (call InitDecoding first)");
+  // faster-decoder.cc:347-354 only: no best-token selection, no backpointer walk; the
+  // answer is kept until the lane's tokens change
+  if (d->rf_cache[lane] < 0) {
+    cudaStream_t s = d->stream;
+    memset(&d->h_items[0], 0, sizeof(kd::AdvanceItem));
+    d->h_items[0].lane = lane;
+    KD_CUDA(cudaMemcpyAsync(d->d_items, d->h_items, sizeof(kd::AdvanceItem),
+                            cudaMemcpyHostToDevice, s));
+    kd::Params P = MakeParams(d);
+    P.items = d->d_items;
+    P.n_items = 1;
+    kd::kd_reached_final_kernel<256><<<1, 256, 0, s>>>(P, d->d_flags);
+    KD_CUDA(cudaGetLastError());
+    KD_CUDA(cudaMemcpyAsync(d->h_flags, d->d_flags, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    KD_CUDA(cudaStreamSynchronize(s));
+    d->rf_cache[lane] = static_cast<int8_t>(d->h_flags[0] != 0);
+  }
+  if (out) *out = d->rf_cache[lane];
   return KD_OK;
 }
 
@@ -1081,11 +1566,13 @@ int kd_decoder_dump_tokens(kd_decoder *d, int32_t lane, int64_t cap, int32_t *st
   int rc = CheckLanes(d, 1, &lane);
   if (rc) return rc;
   KD_CUDA(cudaSetDevice(d->device));
+  rc = WaitLanes(d, 1, &lane);
+  if (rc) return rc;
   if (d->frames[lane] < 0) {
     if (n) *n = 0;
     return KD_OK;
   }
-  rc = FetchLaneStates(d, 1, &lane);
+  rc = FetchLaneStates(d, 1, &lane, d->stream);
   if (rc) return rc;
   const kd::LaneState &L = d->h_lanes[lane];
   if (n) *n = L.n_live;
@@ -1117,6 +1604,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
   if (!d || !out) return Fail(KD_ERR_INVALID, "null argument");
   if (lane >= d->max_lanes) return Fail(KD_ERR_INVALID, "lane id out of range");
   KD_CUDA(cudaSetDevice(d->device));
+  WaitAll(d);
   memset(out, 0, sizeof(*out));
   KD_CUDA(cudaMemcpy(d->h_lanes, d->lanes, sizeof(kd::LaneState) * d->max_lanes,
                      cudaMemcpyDeviceToHost));
@@ -1148,6 +1636,27 @@ int kd_decoder_last_advance_info(kd_decoder *d, float *kernel_ms, int32_t *launc
   if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
   if (kernel_ms) *kernel_ms = d->last_kernel_ms;
   if (launches) *launches = d->last_launches;
+  return KD_OK;
+}
+
+int kd_decoder_span_begin(kd_decoder *d) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  d->span_armed = true;
+  d->span_open = false;
+  d->span_launches = 0;
+  return KD_OK;
+}
+
+int kd_decoder_span_end(kd_decoder *d, float *ms, int32_t *launches) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  KD_CUDA(cudaSetDevice(d->device));
+  int rc = WaitAll(d);
+  if (ms) *ms = 0.f;
+  if (launches) *launches = d->span_launches;
+  const bool open = d->span_open;
+  d->span_armed = d->span_open = false;
+  if (rc) return rc;
+  if (open && ms) KD_CUDA(cudaEventElapsedTime(ms, d->ev_span_begin, d->ev_span_end));
   return KD_OK;
 }
 

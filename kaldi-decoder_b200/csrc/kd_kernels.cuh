@@ -46,7 +46,8 @@ namespace kd {
 constexpr int kStatusHashOverflow = 1;
 constexpr int kStatusArenaOverflow = 2;
 constexpr int kStatusQueueOverflow = 4;
-constexpr int kStatusInputStall = 8;  // streamed log-probs never arrived
+constexpr int kStatusInputStall = 8;  // streamed log-probs never arrived (set by the host)
+constexpr long long kYieldCycles = 40000000;  // ~20 ms of polling before a lane yields
 constexpr int kStatusCandOverflow = 16;  // SimpleDecoder search: candidate buffer full
 
 // In an arc field: "epsilon arc".  In a nextstate field: "state has epsilon arcs".
@@ -113,8 +114,11 @@ struct __align__(16) LaneState {
   float bp_final_w;
   double bp_value;         // selection cost of the best token (cost, or cost + final weight)
   int32_t bp_stored;       // the path's token indices are in the lane's candidate buffer
-  int32_t pad1;
+  int32_t bp_parked;       // the path's arcs are in the lane's worklist buffer: 4 arrays, this far apart
 };
+
+constexpr int32_t kItemInit = 1;      // InitDecoding first (faster-decoder.cc:42-56), in the same launch
+constexpr int32_t kItemFinalize = 2;  // then select the best path and park its arcs (GetBestPath)
 
 struct AdvanceItem {
   int32_t lane;
@@ -122,6 +126,8 @@ struct AdvanceItem {
   int32_t offset;
   int32_t target;       // frames_decoded to reach
   const float *logp;    // device pointer, row-major rows x cols
+  int32_t flags;        // kItem*
+  int32_t path_cap;     // kItemFinalize: arcs per parked array (il | ol | graph | acoustic)
 };
 
 struct Params {
@@ -165,6 +171,7 @@ struct Params {
   // host-memory advance: rows [0, *progress) of every lane's staged matrix have
   // arrived (written by the copy stream while the kernel runs); nullptr = all present
   const int32_t *progress;
+  int32_t *yield_flag;  // set by the first lane that gave up waiting for rows
 };
 
 // ------------------------------------------------------------------ helpers
@@ -235,6 +242,52 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t *total) 
   return s - v;
 }
 
+
+// ---- bulk asynchronous copy (TMA, cp.async.bulk) of one log-prob row into shared memory,
+// completing on an mbarrier.  The copy of frame t+1's row is issued by one thread as soon as
+// frame t's scan is done and lands while the frame's recombination, closure and commit run,
+// so the next frame does not start with a DRAM round trip.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// One thread: expect `bytes` on the barrier and start the copy (16-byte aligned, multiple of 16).
+__device__ __forceinline__ void bulk_load_row(float *dst_smem, const float *src_gmem,
+                                              uint32_t bytes, unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "KD_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra KD_MBAR_DONE;\n\t"
+      "bra KD_MBAR_WAIT;\n\t"
+      "KD_MBAR_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// A row can go through the bulk-copy engine iff its address and size are multiples of 16.
+__device__ __forceinline__ bool row_bulk_ok(const float *row_g, int cols) {
+  return ((reinterpret_cast<uintptr_t>(row_g) | (static_cast<uintptr_t>(cols) * 4u)) & 15u) == 0;
+}
+
 struct Shared {
   double red_d[32];
   int red_i[32];
@@ -261,6 +314,12 @@ struct Shared {
   int status;
   int item;
   int32_t rows_ready;
+  int any_final;           // best-path selection scratch
+  uint32_t best_tok;
+  int row_pending;         // a bulk copy of the next frame's row is in flight
+  uint32_t row_parity;     // phase of row_bar the next wait observes
+  unsigned long long row_bar;  // mbarrier the bulk copy of a log-prob row completes on
+  int yield;  // the lane ran out of streamed rows and gives its CTA back
 };
 
 // min over the block of a double, value only: ordered 64-bit keys, the warp minimum by
@@ -565,16 +624,23 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_number;
+  bool tie_only;
   while (true) {
     const bool cur_is_eps = (cur.arg >> 63) != 0;
+    // Two epsilon arrivals with bit-equal cost: the lower epsilon-arc index wins, so the
+    // backpointer does not depend on thread scheduling (the reference keeps whichever came
+    // first in its LIFO order, faster-decoder.cc:107-112; an incumbent from the emitting
+    // phase stays on a tie in both).
+    tie_only = cur_is_eps && mine.cost == cur.cost && mine.arg < cur.arg;
     // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
-    const bool replace =
-        mine.cost < cur.cost || (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
+    const bool replace = mine.cost < cur.cost || tie_only ||
+                         (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
     if (!replace) return;
     HVal got = cas_hval(&B.table[h].val, cur, mine);
     if (got.cost == cur.cost && got.arg == cur.arg) break;
     cur = got;
   }
+  if (tie_only) return;  // same cost: nothing new to expand
   if (dst_word & kEpsFlag) {
     const uint32_t pos = atomicAdd(q_next_n, 1u);
     if (pos < P.qcap) {
@@ -854,7 +920,8 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
 // new_weight < C* touch the table, so the table holds exactly the tokens.
 template <int THREADS, bool ROW_SMEM, bool SIMPLE>
 __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared &sh,
-                                       LaneState &ls, const float *row_g, float *s_row,
+                                       LaneState &ls, const float *row_g,
+                                       const float *next_row_g, float *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
                                        int32_t *t_tab, uint32_t *t_tok, uint16_t *lab_order,
                                        uint16_t *bin_start) {
@@ -882,13 +949,25 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     seed_sa = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state));
     seed_sb = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state) + 1);
   }
+  // The row is kept as it comes (log-probs); every use negates it (faster-decoder.cc:209).
+  // Usually it is already on its way: the previous frame started a bulk copy (TMA) of it
+  // after its scan.  Rows that cannot go through the bulk-copy engine (address or size not
+  // a multiple of 16 bytes) are loaded by the threads; streamed rows are written by the copy
+  // engine while this kernel runs, so nothing here reads them through the non-coherent path.
   float amin = __int_as_float(0x7F800000);  // smallest acoustic cost of the frame (ROW_SMEM)
+  bool sh_bulk_done = false;
   if (ROW_SMEM) {
-    for (int i = tid; i < P.cols; i += THREADS) {
-      const float v = -__ldg(row_g + i);
-      s_row[i] = v;
-      amin = fminf(amin, v);
+    const bool bulk = sh.row_pending != 0 || row_bulk_ok(row_g, P.cols);  // uniform
+    if (bulk) {
+      if (sh.row_pending == 0 && tid == 0)
+        bulk_load_row(s_row, row_g, static_cast<uint32_t>(P.cols) * 4u, &sh.row_bar);
+      mbar_wait(&sh.row_bar, sh.row_parity);
+    } else {
+      for (int i = tid; i < P.cols; i += THREADS) s_row[i] = __ldcg(row_g + i);
     }
+#pragma unroll 1
+    for (int i = tid; i < P.cols; i += THREADS) amin = fminf(amin, -s_row[i]);
+    if (bulk) sh_bulk_done = true;
   }
   if (tid == 0) {
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
@@ -903,6 +982,10 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   const double ab = static_cast<double>(abf);
   if (tid == 0) sh.wc = wc;
   __syncthreads();
+  if (sh_bulk_done && tid == 0) {  // every thread is past the wait: the barrier's next phase
+    sh.row_parity ^= 1u;
+    sh.row_pending = 0;
+  }
   // Order the frame's labels by acoustic cost (counting sort into 1/16-wide buckets
   // above the minimum).  A token whose slack admits few labels looks those labels up
   // in its state's label table instead of scanning all its arcs.
@@ -917,7 +1000,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     // instruction cache, not of latency hiding here)
 #pragma unroll 1
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = (s_row[i] - amin) * 16.0f;
+      const float d = (-s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
       atomicAdd(&hist[b], 1u);
     }
@@ -958,7 +1041,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     __syncthreads();
 #pragma unroll 1
     for (int i = tid; i < P.cols; i += THREADS) {
-      const float d = (s_row[i] - amin) * 16.0f;
+      const float d = (-s_row[i] - amin) * 16.0f;
       const int b = d < static_cast<float>(kOrderBins - 1) ? static_cast<int>(d) : kOrderBins - 1;
       lab_order[atomicAdd(&hist[b], 1u)] = static_cast<uint16_t>(i + 1);
     }
@@ -979,13 +1062,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         const uint32_t lab = lab_order[tid];
         const int2 ent = __ldg(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
         if (ent.y >= 0)
-          seed = (widen(__int_as_float(ent.x)) + ls.best_cost) + widen(s_row[lab - 1]);
+          seed = (widen(__int_as_float(ent.x)) + ls.best_cost) + widen(-s_row[lab - 1]);
       }
     } else {
 #pragma unroll 1
       for (int a = tid; a < st.y; a += THREADS) {
         const int2 iw = __ldg(P.e_iw + st.x + a);
-        const double ac = widen(ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1));
+        const double ac = widen(-(ROW_SMEM ? s_row[iw.x - 1] : __ldcg(row_g + iw.x - 1)));
         const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
         seed = fmin(seed, nw);
       }
@@ -1195,7 +1278,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         const double cut_d = widen(funkey(*reinterpret_cast<volatile uint32_t *>(&sh.cut_fkey)));
 #pragma unroll
         for (int u = 0; u < kWin; ++u) {
-          const double ac = widen(ROW_SMEM ? s_row[iw[u].x - 1] : -__ldg(row_g + iw[u].x - 1));
+          const double ac = widen(-(ROW_SMEM ? s_row[iw[u].x - 1] : __ldcg(row_g + iw[u].x - 1)));
           const double tcst = t_cost[min(tt[u], static_cast<uint32_t>(TT - 1))];
           const double nw = (widen(__int_as_float(iw[u].y)) + tcst) + ac;
           // faster-decoder.cc:211 against the running cutoff
@@ -1240,6 +1323,12 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   const double bmin = block_min<THREADS>(fmin(my_min, seed), sh, 0);
   const double cstar = bmin + ab;
   const unsigned long long cstar_key = dkey(cstar);
+  // every thread is done with this frame's row (the barrier in block_min): the next frame's
+  // row can take its place while the candidates are recombined and the frame is closed
+  if (!SIMPLE && ROW_SMEM && next_row_g != nullptr && tid == 0) {
+    bulk_load_row(s_row, next_row_g, static_cast<uint32_t>(P.cols) * 4u, &sh.row_bar);
+    sh.row_pending = 1;
+  }
   // ---------------------------------------------------------------- recombine
   const uint32_t n_cand = min(sh.cand_n, P.ccap);
   if (tid == 0) ls.st_cand += sh.cand_n;
@@ -1255,7 +1344,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       // SimpleDecoder prunes on (cost + w) + ac but stores cost + float(w + ac)
       // (simple-decoder.cc:168 vs simple-decoder.h:96)
       const int2 iw = __ldg(P.e_iw + c.z);
-      const float ac = ROW_SMEM ? s_row[iw.x - 1] : -__ldg(row_g + iw.x - 1);
+      const float ac = -(ROW_SMEM ? s_row[iw.x - 1] : __ldcg(row_g + iw.x - 1));
       const double stored = B.a_cost[c.w] + static_cast<double>(__fadd_rn(__int_as_float(iw.y), ac));
       min_stored = fmin(min_stored, stored);
       nk = dkey(stored);
@@ -1302,242 +1391,30 @@ constexpr int advance_max_regs(int threads, int min_blocks) {
   return r > 255 ? 255 : r;
 }
 
-template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM, bool SIMPLE = false>
-__global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS, MIN_BLOCKS))
-    kd_advance_kernel(Params P) {
-  constexpr int TT = THREADS * kTileTokens;
-  __shared__ Shared sh;
-  __shared__ LaneState ls;
-  __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
-  const LaneBuf &B = sB;
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  double *t_cost = reinterpret_cast<double *>(dyn_smem);
-  uint32_t *t_beg = reinterpret_cast<uint32_t *>(t_cost + TT);
-  uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
-  int32_t *t_tab = reinterpret_cast<int32_t *>(t_ex + TT + 4);
-  uint32_t *t_tok = reinterpret_cast<uint32_t *>(t_tab + TT);
-  uint16_t *bin_start = reinterpret_cast<uint16_t *>(t_tok + TT);  // kOrderBins + 2 entries
-  float *s_row = reinterpret_cast<float *>(bin_start + kOrderBins + 8);  // 4-byte aligned
-  // the label order (one uint16 per column) follows the row
-  const int tid = threadIdx.x;
-
-  while (true) {
-    if (tid == 0) sh.item = atomicAdd(P.work_counter, 1);
-    __syncthreads();
-    const int item = sh.item;
-    if (item >= P.n_items) return;
-    const AdvanceItem it = P.items[item];
-    if (tid == 0) {
-      sB = lane_buffers(P, it.lane);
-      ls = P.lanes[it.lane];
-      sh.status = ls.status;
-      sh.list_n = 0;
-      sh.q_n[0] = 0;
-      sh.rows_ready = P.progress != nullptr ? 0 : 0x7FFFFFFF;
-    }
-    __syncthreads();
-    while (ls.frames_decoded < it.target && sh.status == 0) {
-      const int frame = ls.frames_decoded;
-      if (frame - it.offset >= sh.rows_ready) {
-        // the row has not been seen to arrive yet: poll the copy stream's progress word
-        __syncthreads();  // every thread has read rows_ready before thread 0 rewrites it
-        if (tid == 0) {
-          const volatile int32_t *pr = P.progress;
-          int32_t ready = *pr;
-          for (uint32_t spins = 0; ready <= frame - it.offset; ++spins) {
-            if (spins > (1u << 24)) {  // ~4 s: the copies are not coming
-              sh.status |= kStatusInputStall;
-              break;
-            }
-            __nanosleep(256);
-            ready = *pr;
-          }
-          __threadfence();
-          sh.rows_ready = ready;
-        }
-        __syncthreads();
-        if (sh.status != 0) break;
-      }
-      const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
-      const int n_in = ls.n_live;
-      uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
-      const double cstar = lane_expand_emitting<THREADS, ROW_SMEM, SIMPLE>(
-          P, B, sh, ls, row_g, s_row, t_cost, t_ex, t_beg, t_tab, t_tok, lab_order, bin_start);
-      // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
-      lane_closure_and_commit<THREADS, SIMPLE>(P, B, sh, ls, cstar,
-                                       cstar - 0.75 * static_cast<double>(P.beam),
-                                       cstar - 0.25 * static_cast<double>(P.beam));
-      if (tid == 0) {
-        ls.frames_decoded = frame + 1;
-        ls.st_frames += 1;
-        ls.st_tokens_in += n_in;
-        ls.st_tokens_out += ls.n_live;
-        ls.st_emit_arcs += sh.acc_emit;
-        ls.st_expanded += sh.acc_expanded;
-        ls.st_items += sh.acc_items;
-        if (ls.n_live > ls.st_max_tokens) ls.st_max_tokens = ls.n_live;
-      }
-      __syncthreads();
-    }
-    if (tid == 0) {
-      ls.status = sh.status;
-      P.lanes[it.lane] = ls;
-    }
-    __syncthreads();
-  }
+// The start token (faster-decoder.cc:46-52): cost 0 at Start(), no arc, no predecessor.
+// One thread; the caller closes it over the epsilon arcs and commits.
+__device__ __forceinline__ void lane_start_token(const Params &P, const LaneBuf &B, Shared &sh) {
+  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(P.start));
+  const uint32_t h = table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
+  if (h == kNoIdx) return;
+  HVal v;
+  v.cost = dkey(0.0);
+  v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
+  *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
 }
 
-// InitDecoding (faster-decoder.cc:42-56): start token with cost 0, epsilon
-// closure under cutoff FLT_MAX, zero frames decoded.  items[i].lane = lane.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
-  __shared__ Shared sh;
-  __shared__ LaneState ls;
-  const int tid = threadIdx.x;
-  const int item = blockIdx.x;
-  if (item >= P.n_items) return;
-  const int lane = P.items[item].lane;
-  const LaneBuf B = lane_buffers(P, lane);
-  if (tid == 0) {
-    LaneState z;
-    memset(&z, 0, sizeof(z));
-    z.frames_decoded = 0;
-    z.best_cost = __longlong_as_double(0x7FF0000000000000ll);
-    z.best_idx = -1;
-    z.best_state = -1;
-    ls = z;
-    sh.status = 0;
-    sh.list_n = 0;
-    sh.q_n[0] = 0;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const int4 st = __ldg(P.st + 2 * static_cast<size_t>(P.start));
-    const uint32_t h =
-        table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
-    HVal v;
-    v.cost = dkey(0.0);
-    v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
-    *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
-  }
-  __syncthreads();
-  if (P.simple) {
-    // SimpleDecoder::InitDecoding: closure under cutoff 0 + beam (simple-decoder.cc:29-41,196-204)
-    lane_closure_and_commit<THREADS, true>(P, B, sh, ls, static_cast<double>(P.beam), 0.0, 0.0);
-  } else {
-    lane_closure_and_commit<THREADS, false>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */,
-                                            0.0, 0.0);
-  }
-  if (tid == 0) {
-    ls.status = sh.status;
-    ls.st_sweeps = 0;
-    ls.st_eps_arcs = 0;
-    ls.cyc_closure = ls.cyc_commit = 0;
-    ls.st_claimed = 0;
-    P.lanes[lane] = ls;
-  }
+__device__ __forceinline__ void lane_state_reset(LaneState &ls) {
+  // (word by word, in place: a local copy of the struct would live on the stack)
+  uint32_t *w = reinterpret_cast<uint32_t *>(&ls);
+#pragma unroll 1
+  for (int i = 0; i < static_cast<int>(sizeof(LaneState) / 4); ++i) w[i] = 0u;
+  ls.best_cost = __longlong_as_double(0x7FF0000000000000ll);
+  ls.best_idx = -1;
+  ls.best_state = -1;
 }
 
-// ReachedFinal + best-token selection + path length (faster-decoder.cc:347-402).
-// Ties on the selection cost go to the lowest state id.
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) kd_best_select_kernel(Params P) {
-  __shared__ Shared sh;
-  __shared__ int s_any_final;
-  __shared__ uint32_t s_best_tok;
-  const int tid = threadIdx.x;
-  const int lane = P.items[blockIdx.x].lane;
-  const LaneBuf B = lane_buffers(P, lane);
-  LaneState *L = P.lanes + lane;
-  const int n = L->n_tok;
-  const uint32_t base = L->tok_base;
-  const double inf = __longlong_as_double(0x7FF0000000000000ll);
-  if (tid == 0) {
-    s_any_final = 0;
-    s_best_tok = kNoIdx;
-  }
-  __syncthreads();
-  // SimpleDecoder::PruneToks (simple-decoder.cc:251-279) runs after every frame: only
-  // tokens with cost < best + beam exist for ReachedFinal / GetBestPath.  The search
-  // applies the same test when it expands the next frame; here it is applied to the view.
-  const double limit = (P.simple && L->frames_decoded > 0)
-                           ? L->best_cost + static_cast<double>(P.beam)
-                           : inf;
-  const bool pruned_view = P.simple && L->frames_decoded > 0;
-  int any = 0;
-  for (int i = tid; i < n; i += THREADS) {
-    const int s = B.a_state[base + i];
-    if (s < 0) continue;  // a hole, not a token
-    const double c = B.a_cost[base + i];
-    if (pruned_view && !(c < limit)) continue;
-    float f = __ldg(P.fin + s);
-    if (c != inf && f != __int_as_float(0x7F800000)) any = 1;
-  }
-  if (any) atomicOr(&s_any_final, 1);
-  __syncthreads();
-  const int is_final = s_any_final;
-  double bv = inf;
-  int bs = -1;  // state id is the tie-break key; token index recovered below
-  for (int i = tid; i < n; i += THREADS) {
-    int s = B.a_state[base + i];
-    if (s < 0) continue;
-    double c = B.a_cost[base + i];
-    if (pruned_view && !(c < limit)) continue;
-    double v = is_final ? c + static_cast<double>(__ldg(P.fin + s)) : c;
-    bool take = is_final ? (v != inf) : true;
-    if (take && (bs < 0 || v < bv || (v == bv && s < bs))) {
-      bv = v;
-      bs = s;
-    }
-  }
-  double rv;
-  int rs;
-  // block_min_arg treats idx -1 as "none" (largest unsigned)
-  block_min_arg<THREADS>(bs < 0 ? inf : bv, bs, sh, &rv, &rs);
-  if (rs >= 0) {
-    for (int i = tid; i < n; i += THREADS)
-      if (B.a_state[base + i] == rs) s_best_tok = base + i;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    L->bp_final = is_final;
-    if (rs < 0 || s_best_tok == kNoIdx) {
-      L->bp_ok = 0;
-      L->bp_len = 0;
-      L->bp_best_tok = kNoIdx;
-      L->bp_best_state = -1;
-      L->bp_final_w = 0.f;
-      L->bp_value = inf;
-    } else {
-      L->bp_value = rv;
-      // The only walk of the backpointer chain: the token indices met on the way are
-      // parked in the lane's candidate buffer (idle between AdvanceDecoding calls), so
-      // the arcs can then be written out by all threads at once.
-      uint32_t *path = reinterpret_cast<uint32_t *>(B.cand);
-      const long long path_cap = 4ll * P.ccap;
-      long long len = 0;
-      uint32_t t = s_best_tok;
-      while (true) {
-        unsigned long long link = B.a_link[t];
-        uint32_t arc = static_cast<uint32_t>(link >> 32);
-        if (arc == kNoArc) break;
-        if (len < path_cap) path[len] = t;
-        ++len;
-        t = static_cast<uint32_t>(link);
-      }
-      L->bp_ok = 1;
-      L->bp_stored = len <= path_cap ? 1 : 0;
-      L->bp_len = len;
-      L->bp_best_tok = s_best_tok;
-      L->bp_best_state = rs;
-      L->bp_final_w = __ldg(P.fin + rs);
-    }
-  }
-}
-
-// Writes the best path of lane items[b].lane in time order at out_off[b]
-// (faster-decoder.cc:393-402: graph = arc weight, acoustic = float(cost -
-// prev cost) - graph).
+// Writes one arc of the best path (faster-decoder.cc:393-402: graph = arc weight,
+// acoustic = float(cost - prev cost) - graph).
 __device__ __forceinline__ void write_path_arc(const Params &P, uint32_t arc, double c, double pc,
                                                long long pos, int32_t *il, int32_t *ol, float *gw,
                                                float *aw) {
@@ -1562,19 +1439,119 @@ __device__ __forceinline__ void write_path_arc(const Params &P, uint32_t arc, do
   aw[pos] = tot - graph;
 }
 
-// One CTA per lane.  With the token indices of the path at hand (kd_best_select_kernel)
-// every arc is independent; otherwise (path longer than the buffer) thread 0 walks the chain.
-__global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t *il, int32_t *ol,
-                                    float *gw, float *aw) {
-  const int b = blockIdx.x;
-  if (b >= P.n_items) return;
-  const int lane = P.items[b].lane;
-  const LaneBuf B = lane_buffers(P, lane);
-  const LaneState *L = P.lanes + lane;
-  if (!L->bp_ok) return;
-  const long long len = L->bp_len;
-  const long long last = out_off[b] + len - 1;
-  if (L->bp_stored) {
+// ReachedFinal (faster-decoder.cc:347-354): does a live token sit in a final state?
+// All threads return the answer.  SimpleDecoder::PruneToks (simple-decoder.cc:251-279)
+// runs after every frame: only tokens with cost < best + beam exist for ReachedFinal /
+// GetBestPath.  The search applies the same test when it expands the next frame; here it
+// is applied to the view.
+template <int THREADS>
+__device__ int lane_reached_final(const Params &P, const LaneBuf &B, Shared &sh,
+                                  const LaneState &L) {
+  const int tid = threadIdx.x;
+  const int n = L.n_tok;
+  const uint32_t base = L.tok_base;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  const bool pruned_view = P.simple && L.frames_decoded > 0;
+  const double limit = pruned_view ? L.best_cost + static_cast<double>(P.beam) : inf;
+  if (tid == 0) sh.any_final = 0;
+  __syncthreads();
+  int any = 0;
+  for (int i = tid; i < n; i += THREADS) {
+    const int s = B.a_state[base + i];
+    if (s < 0) continue;  // a hole, not a token
+    const double c = B.a_cost[base + i];
+    if (pruned_view && !(c < limit)) continue;
+    const float f = __ldg(P.fin + s);
+    if (c != inf && f != __int_as_float(0x7F800000)) any = 1;
+  }
+  if (any) atomicOr(&sh.any_final, 1);
+  __syncthreads();
+  return sh.any_final;
+}
+
+// ReachedFinal + best-token selection + the one walk of the backpointer chain
+// (faster-decoder.cc:347-402).  Ties on the selection cost go to the lowest state id.
+// The token indices met on the walk are parked in the lane's candidate buffer (idle
+// between frames), so the arcs can then be written out by all threads at once.
+template <int THREADS>
+__device__ __noinline__ void lane_select_best(const Params &P, const LaneBuf &B, Shared &sh,
+                                              LaneState &L) {
+  const int tid = threadIdx.x;
+  const int n = L.n_tok;
+  const uint32_t base = L.tok_base;
+  const double inf = __longlong_as_double(0x7FF0000000000000ll);
+  const bool pruned_view = P.simple && L.frames_decoded > 0;
+  const double limit = pruned_view ? L.best_cost + static_cast<double>(P.beam) : inf;
+  const int is_final = lane_reached_final<THREADS>(P, B, sh, L);
+  if (tid == 0) sh.best_tok = kNoIdx;
+  double bv = inf;
+  int bs = -1;  // state id is the tie-break key; token index recovered below
+  for (int i = tid; i < n; i += THREADS) {
+    const int s = B.a_state[base + i];
+    if (s < 0) continue;
+    const double c = B.a_cost[base + i];
+    if (pruned_view && !(c < limit)) continue;
+    const double v = is_final ? c + static_cast<double>(__ldg(P.fin + s)) : c;
+    const bool take = is_final ? (v != inf) : true;
+    if (take && (bs < 0 || v < bv || (v == bv && s < bs))) {
+      bv = v;
+      bs = s;
+    }
+  }
+  double rv;
+  int rs;
+  // block_min_arg treats idx -1 as "none" (largest unsigned)
+  block_min_arg<THREADS>(bs < 0 ? inf : bv, bs, sh, &rv, &rs);
+  if (rs >= 0) {
+    for (int i = tid; i < n; i += THREADS)
+      if (B.a_state[base + i] == rs) sh.best_tok = base + i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    L.bp_final = is_final;
+    L.bp_parked = 0;
+    if (rs < 0 || sh.best_tok == kNoIdx) {
+      L.bp_ok = 0;
+      L.bp_len = 0;
+      L.bp_stored = 0;
+      L.bp_best_tok = kNoIdx;
+      L.bp_best_state = -1;
+      L.bp_final_w = 0.f;
+      L.bp_value = inf;
+    } else {
+      L.bp_value = rv;
+      uint32_t *path = reinterpret_cast<uint32_t *>(B.cand);
+      const long long path_cap = 4ll * P.ccap;
+      long long len = 0;
+      uint32_t t = sh.best_tok;
+      while (true) {
+        const unsigned long long link = B.a_link[t];
+        const uint32_t arc = static_cast<uint32_t>(link >> 32);
+        if (arc == kNoArc) break;
+        if (len < path_cap) path[len] = t;
+        ++len;
+        t = static_cast<uint32_t>(link);
+      }
+      L.bp_ok = 1;
+      L.bp_stored = len <= path_cap ? 1 : 0;
+      L.bp_len = len;
+      L.bp_best_tok = sh.best_tok;
+      L.bp_best_state = rs;
+      L.bp_final_w = __ldg(P.fin + rs);
+    }
+  }
+  __syncthreads();
+}
+
+// Writes the arcs of the selected path, in time order, into four arrays starting at
+// il/ol/gw/aw[first].  With the token indices of the path at hand every arc is independent;
+// otherwise (path longer than the candidate buffer) thread 0 walks the chain again.
+__device__ __forceinline__ void lane_write_path(const Params &P, const LaneBuf &B,
+                                                const LaneState &L, long long first, int32_t *il,
+                                                int32_t *ol, float *gw, float *aw) {
+  const long long len = L.bp_len;
+  const long long last = first + len - 1;
+  if (L.bp_stored) {
     const uint32_t *path = reinterpret_cast<const uint32_t *>(B.cand);
     for (long long i = threadIdx.x; i < len; i += blockDim.x) {
       const uint32_t t = path[i];
@@ -1587,23 +1564,246 @@ __global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t 
   }
   if (threadIdx.x != 0) return;
   long long pos = last;
-  uint32_t t = L->bp_best_tok;
+  uint32_t t = L.bp_best_tok;
   double c = B.a_cost[t];
   unsigned long long link = B.a_link[t];
   while (true) {
-    uint32_t arc = static_cast<uint32_t>(link >> 32);
+    const uint32_t arc = static_cast<uint32_t>(link >> 32);
     if (arc == kNoArc) break;
-    uint32_t prev = static_cast<uint32_t>(link);
+    const uint32_t prev = static_cast<uint32_t>(link);
     // the pointer chase is the critical path: its next load goes out before the
     // loads that only feed this step's output
     const unsigned long long link_next = B.a_link[prev];
-    double pc = B.a_cost[prev];
+    const double pc = B.a_cost[prev];
     write_path_arc(P, arc, c, pc, pos, il, ol, gw, aw);
     --pos;
     t = prev;
     c = pc;
     link = link_next;
   }
+}
+
+// kItemFinalize: GetBestPath inside the search launch.  The lane's CTA selects the best
+// token, walks its backpointers and parks the path's arcs in the lane's epsilon-worklist
+// buffer (idle once the last frame is committed) as four arrays of `path_cap` words
+// [ilabel | olabel | graph | acoustic]; the host then fetches them with plain copies and
+// no further kernel.  A path that does not fit stays unparked (the host falls back to
+// kd_best_fill_kernel).
+template <int THREADS>
+__device__ __noinline__ void lane_finalize(const Params &P, const LaneBuf &B, Shared &sh,
+                                           LaneState &L, int32_t path_cap) {
+  lane_select_best<THREADS>(P, B, sh, L);
+  if (!L.bp_ok) return;
+  const long long room = path_cap < static_cast<long long>(P.qcap / 2) ? path_cap : P.qcap / 2;
+  if (L.bp_len > room || path_cap <= 0) return;
+  int32_t *out = reinterpret_cast<int32_t *>(B.queue);
+  lane_write_path(P, B, L, 0, out, out + path_cap, reinterpret_cast<float *>(out + 2 * path_cap),
+                  reinterpret_cast<float *>(out + 3 * path_cap));
+  __syncthreads();
+  if (threadIdx.x == 0) L.bp_parked = path_cap;
+}
+
+template <int THREADS, int MIN_BLOCKS, bool ROW_SMEM, bool SIMPLE = false>
+__global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS, MIN_BLOCKS))
+    kd_advance_kernel(const __grid_constant__ Params P) {
+  constexpr int TT = THREADS * kTileTokens;
+  __shared__ Shared sh;
+  __shared__ LaneState ls;
+  __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
+  const LaneBuf &B = sB;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  double *t_cost = reinterpret_cast<double *>(dyn_smem);
+  uint32_t *t_beg = reinterpret_cast<uint32_t *>(t_cost + TT);
+  uint32_t *t_ex = t_beg + TT;  // TT + 1 entries (+ pad to 4)
+  int32_t *t_tab = reinterpret_cast<int32_t *>(t_ex + TT + 4);
+  uint32_t *t_tok = reinterpret_cast<uint32_t *>(t_tab + TT);
+  uint16_t *bin_start = reinterpret_cast<uint16_t *>(t_tok + TT);  // kOrderBins + 2 entries
+  float *s_row = reinterpret_cast<float *>(bin_start + kOrderBins + 8);  // 16-byte aligned
+  // the label order (one uint16 per column) follows the row
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&sh.row_bar, 1);
+    sh.row_parity = 0;
+    sh.row_pending = 0;
+  }
+  __syncthreads();
+
+  while (true) {
+    if (tid == 0) sh.item = atomicAdd(P.work_counter, 1);
+    __syncthreads();
+    const int item = sh.item;
+    if (item >= P.n_items) return;
+    const AdvanceItem it = P.items[item];
+    // InitDecoding in the same launch: the first pass of the loop below has no emitting
+    // phase -- the start token is closed over the epsilon arcs under FLT_MAX
+    // (faster-decoder.cc:53; SimpleDecoder: under 0 + beam, simple-decoder.cc:29-41)
+    bool init_pass = (it.flags & kItemInit) != 0;
+    if (tid == 0) {
+      sB = lane_buffers(P, it.lane);
+      if (init_pass) {
+        lane_state_reset(ls);
+      } else {
+        ls = P.lanes[it.lane];
+      }
+      sh.status = ls.status;
+      sh.list_n = 0;
+      sh.q_n[0] = 0;
+      sh.rows_ready = P.progress != nullptr ? 0 : 0x7FFFFFFF;
+      sh.yield = 0;
+    }
+    __syncthreads();
+    while (true) {
+      double cstar, good_cut, mid_cut;
+      int n_in = 0, frame = 0;
+      if (init_pass) {
+        if (tid == 0) lane_start_token(P, B, sh);
+        cstar = SIMPLE ? static_cast<double>(P.beam) : 3.4028234663852886e+38 /* FLT_MAX */;
+        good_cut = mid_cut = 0.0;
+        __syncthreads();
+      } else {
+        if (!(ls.frames_decoded < it.target && sh.status == 0)) break;
+        frame = ls.frames_decoded;
+        if (frame - it.offset >= sh.rows_ready) {
+          // the row has not been seen to arrive yet: poll the copy stream's progress word
+          __syncthreads();  // every thread has read rows_ready before thread 0 rewrites it
+          if (tid == 0) {
+            const volatile int32_t *pr = P.progress;
+            volatile int32_t *fl = P.yield_flag;
+            int32_t ready = *pr;
+            const long long t0 = clock64();
+            while (ready <= frame - it.offset) {
+              // Nothing for ~20 ms: the copies are not coming while this kernel runs
+              // (launches are serialised -- CUDA_LAUNCH_BLOCKING, a profiler -- or the host
+              // is staging pageable memory).  The lane yields: its state is saved as it is
+              // and the host launches again once the copies are enqueued.
+              if (clock64() - t0 > kYieldCycles || *fl != 0) {
+                sh.yield = 1;
+                *fl = 1;  // the other lanes need not wait as long
+                break;
+              }
+              __nanosleep(256);
+              ready = *pr;
+            }
+            __threadfence();
+            sh.rows_ready = ready;
+          }
+          __syncthreads();
+          if (sh.yield != 0) break;
+        }
+        const float *row_g = it.logp + static_cast<size_t>(frame - it.offset) * P.cols;
+        // the next frame's row, if it is known to be there and fit for a bulk copy
+        const float *next_row_g = nullptr;
+        if (ROW_SMEM && frame + 1 < it.target && frame + 1 - it.offset < sh.rows_ready &&
+            row_bulk_ok(row_g + P.cols, P.cols))
+          next_row_g = row_g + P.cols;
+        n_in = ls.n_live;
+        uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
+        cstar = lane_expand_emitting<THREADS, ROW_SMEM, SIMPLE>(P, B, sh, ls, row_g, next_row_g,
+                                                                s_row, t_cost, t_ex, t_beg, t_tab,
+                                                                t_tok, lab_order, bin_start);
+        // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
+        good_cut = cstar - 0.75 * static_cast<double>(P.beam);
+        mid_cut = cstar - 0.25 * static_cast<double>(P.beam);
+      }
+      lane_closure_and_commit<THREADS, SIMPLE>(P, B, sh, ls, cstar, good_cut, mid_cut);
+      if (tid == 0) {
+        if (init_pass) {
+          ls.st_sweeps = 0;
+          ls.st_eps_arcs = 0;
+          ls.cyc_closure = ls.cyc_commit = 0;
+          ls.st_claimed = 0;
+        } else {
+          ls.frames_decoded = frame + 1;
+          ls.st_frames += 1;
+          ls.st_tokens_in += n_in;
+          ls.st_tokens_out += ls.n_live;
+          ls.st_emit_arcs += sh.acc_emit;
+          ls.st_expanded += sh.acc_expanded;
+          ls.st_items += sh.acc_items;
+          if (ls.n_live > ls.st_max_tokens) ls.st_max_tokens = ls.n_live;
+        }
+      }
+      init_pass = false;
+      __syncthreads();
+    }
+    if ((it.flags & kItemFinalize) != 0 && sh.status == 0 && sh.yield == 0 &&
+        ls.frames_decoded >= it.target)
+      lane_finalize<THREADS>(P, B, sh, ls, it.path_cap);
+    if (tid == 0) {
+      ls.status = sh.status;
+      P.lanes[it.lane] = ls;
+    }
+    __syncthreads();
+  }
+}
+
+// InitDecoding alone (faster-decoder.cc:42-56): start token with cost 0, epsilon
+// closure under cutoff FLT_MAX, zero frames decoded.  items[i].lane = lane.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
+  __shared__ Shared sh;
+  __shared__ LaneState ls;
+  const int tid = threadIdx.x;
+  const int item = blockIdx.x;
+  if (item >= P.n_items) return;
+  const int lane = P.items[item].lane;
+  const LaneBuf B = lane_buffers(P, lane);
+  if (tid == 0) {
+    lane_state_reset(ls);
+    sh.status = 0;
+    sh.list_n = 0;
+    sh.q_n[0] = 0;
+  }
+  __syncthreads();
+  if (tid == 0) lane_start_token(P, B, sh);
+  __syncthreads();
+  if (P.simple) {
+    // SimpleDecoder::InitDecoding: closure under cutoff 0 + beam (simple-decoder.cc:29-41,196-204)
+    lane_closure_and_commit<THREADS, true>(P, B, sh, ls, static_cast<double>(P.beam), 0.0, 0.0);
+  } else {
+    lane_closure_and_commit<THREADS, false>(P, B, sh, ls, 3.4028234663852886e+38 /* FLT_MAX */,
+                                            0.0, 0.0);
+  }
+  if (tid == 0) {
+    ls.status = sh.status;
+    ls.st_sweeps = 0;
+    ls.st_eps_arcs = 0;
+    ls.cyc_closure = ls.cyc_commit = 0;
+    ls.st_claimed = 0;
+    P.lanes[lane] = ls;
+  }
+}
+
+// GetBestPath step 1 as a kernel of its own (lanes that were not finalized by their last
+// search launch: partial results while streaming).  One CTA per lane.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) kd_best_select_kernel(const __grid_constant__ Params P) {
+  __shared__ Shared sh;
+  const int lane = P.items[blockIdx.x].lane;
+  const LaneBuf B = lane_buffers(P, lane);
+  lane_select_best<THREADS>(P, B, sh, P.lanes[lane]);
+}
+
+// ReachedFinal alone: no backpointer walk.  out[b] = flag of lane items[b].lane.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) kd_reached_final_kernel(Params P, int32_t *out) {
+  __shared__ Shared sh;
+  const int lane = P.items[blockIdx.x].lane;
+  const LaneBuf B = lane_buffers(P, lane);
+  const int f = lane_reached_final<THREADS>(P, B, sh, P.lanes[lane]);
+  if (threadIdx.x == 0) out[blockIdx.x] = f;
+}
+
+// GetBestPath step 2: the best path of lane items[b].lane in time order at out_off[b].
+__global__ void kd_best_fill_kernel(Params P, const long long *out_off, int32_t *il, int32_t *ol,
+                                    float *gw, float *aw) {
+  const int b = blockIdx.x;
+  if (b >= P.n_items) return;
+  const int lane = P.items[b].lane;
+  const LaneBuf B = lane_buffers(P, lane);
+  const LaneState *L = P.lanes + lane;
+  if (!L->bp_ok) return;
+  lane_write_path(P, B, *L, out_off[b], il, ol, gw, aw);
 }
 
 }  // namespace kd

@@ -22,6 +22,8 @@ KD_OK = 0
 KD_SEARCH_FASTER, KD_SEARCH_SIMPLE = 0, 1
 KD_MEM_HOST = 0
 KD_MEM_DEVICE = 1
+KD_ADVANCE_INIT = 1
+KD_ADVANCE_FINALIZE = 2
 INT32_MAX = 2**31 - 1
 
 
@@ -54,7 +56,8 @@ EXPORTED = (
     "kd_decoder_best_path_prepare", "kd_decoder_best_path_fetch", "kd_decoder_best_path_view",
     "kd_decoder_best_path",
     "kd_decoder_dump_tokens", "kd_decoder_stats", "kd_decoder_last_advance_info",
-    "kd_decoder_info", "kd_decoder_final_relative_cost",
+    "kd_decoder_info", "kd_decoder_final_relative_cost", "kd_decoder_advance_async",
+    "kd_decoder_wait", "kd_decoder_result_view", "kd_decoder_span_begin", "kd_decoder_span_end",
 )
 
 _lib = None
@@ -92,6 +95,13 @@ def lib():
         L.kd_decoder_last_advance_info.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
         L.kd_decoder_info.argtypes = [vp, vp]
         L.kd_decoder_final_relative_cost.argtypes = [vp, i32, C.POINTER(C.c_float)]
+        L.kd_decoder_advance_async.argtypes = [vp, i32, vp, vp, vp, i32, vp, i32, C.c_int, C.c_int,
+                                               vp, C.POINTER(i64)]
+        L.kd_decoder_wait.argtypes = [vp, i64]
+        L.kd_decoder_span_begin.argtypes = [vp]
+        L.kd_decoder_span_end.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(i32)]
+        L.kd_decoder_result_view.argtypes = [vp, i64, C.c_int, C.POINTER(i32), C.POINTER(vp),
+                                             C.POINTER(vp), C.POINTER(vp), vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -180,12 +190,15 @@ class RawPath:
 
 
 class PathBatch:
-    """The best paths of a batch of lanes: flat arc arrays + offsets; item i is a RawPath
-    (views into the flat arrays, no per-lane copies)."""
+    """The best paths of a batch of lanes.  All arcs live in one int32 word buffer; lane i's
+    four arrays (ilabel, olabel, graph, acoustic) are `lens[i]` words each, starting at
+    `word_offsets[i, 0..3]`.  Item i is a RawPath (views, no per-lane copies)."""
 
-    def __init__(self, ok, reached_final, offsets, il, ol, gw, aw, final):
-        self.ok, self.reached_final, self.offsets = ok, reached_final, offsets
-        self.ilabels, self.olabels, self.graph, self.acoustic, self.final = il, ol, gw, aw, final
+    def __init__(self, ok, reached_final, lens, words, word_offsets, final, d2h_bytes=0):
+        self.ok, self.reached_final, self.lens = ok, reached_final, lens
+        self.words, self.word_offsets, self.final = words, word_offsets, final
+        self._fwords = words.view(np.float32)
+        self.d2h_bytes = int(d2h_bytes)  # bytes the device->host copy of these paths moved
 
     def __len__(self):
         return int(self.ok.shape[0])
@@ -197,9 +210,11 @@ class PathBatch:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
-        return RawPath(self.ok[i], self.reached_final[i], self.ilabels[a:b], self.olabels[a:b],
-                       self.graph[a:b], self.acoustic[a:b], self.final[i])
+        n = int(self.lens[i])
+        o = self.word_offsets[i]
+        return RawPath(self.ok[i], self.reached_final[i], self.words[int(o[0]):int(o[0]) + n],
+                       self.words[int(o[1]):int(o[1]) + n], self._fwords[int(o[2]):int(o[2]) + n],
+                       self._fwords[int(o[3]):int(o[3]) + n], self.final[i])
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
@@ -290,14 +305,82 @@ class LaneDecoder:
         _check(lib().kd_decoder_best_path_view(self.h, n, la.ctypes.data, off.ctypes.data, total,
                                                C.byref(ptr[0]), C.byref(ptr[1]), C.byref(ptr[2]),
                                                C.byref(ptr[3]), f2.ctypes.data))
-        arrs = []
-        for p, dt in zip(ptr, (np.int32, np.int32, np.float32, np.float32)):
-            if total == 0 or not p.value:
-                arrs.append(np.empty(0, dt))
-                continue
-            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_int32)), shape=(total,)).view(dt)
-            arrs.append(a.copy() if copy else a)
-        return PathBatch(ok, rf, off, arrs[0], arrs[1], arrs[2], arrs[3], f2)
+        if total == 0 or not ptr[0].value:
+            words = np.empty(0, np.int32)
+        else:
+            # the four arrays are `total` words apart in one pinned buffer
+            words = np.ctypeslib.as_array(C.cast(ptr[0], C.POINTER(C.c_int32)), shape=(4 * total,))
+            if copy:
+                words = words.copy()
+        woff = off[:n, None] + (np.arange(4, dtype=np.int64) * total)[None, :]
+        return PathBatch(ok, rf, cnt, words, woff, f2, d2h_bytes=16 * total)
+
+    # ---- asynchronous calls (kd_decoder_advance_async / _wait / _result_view)
+
+    def advance_async(self, lanes, ptrs: Sequence[int], rows, cols: int, offsets=None,
+                      max_num_frames: int = -1, mem_kind: int = KD_MEM_HOST, init: bool = False,
+                      finalize: bool = False, producer_stream: int = 0) -> int:
+        """Enqueues AdvanceDecoding (optionally with InitDecoding before and the best-path
+        selection after it, all in one kernel launch) and returns a ticket."""
+        la = self._lanes(lanes)
+        pa = (C.c_void_p * la.size)(*[int(p) for p in ptrs])
+        ra = np.ascontiguousarray(rows, dtype=np.int32).reshape(-1)
+        oa = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1)
+        flags = (KD_ADVANCE_INIT if init else 0) | (KD_ADVANCE_FINALIZE if finalize else 0)
+        t = C.c_int64(-1)
+        _check(lib().kd_decoder_advance_async(
+            self.h, la.size, la.ctypes.data, pa, ra.ctypes.data, int(cols),
+            None if oa is None else oa.ctypes.data, int(max_num_frames), int(mem_kind), flags,
+            C.c_void_p(int(producer_stream) or None), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int = -1):
+        _check(lib().kd_decoder_wait(self.h, int(ticket)))
+
+    def results(self, ticket: int, use_final_probs: bool = True, copy: bool = True) -> "PathBatch":
+        """Best paths of a finalize=True call.  copy=False returns views of the decoder's
+        pinned result buffer (valid until the third-next advance_async call)."""
+        n = C.c_int32(0)
+        lp, wp, op = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        cap = self.max_lanes
+        ok = np.zeros(cap, np.int32)
+        rf = np.zeros(cap, np.int32)
+        cnt = np.zeros(cap, np.int64)
+        f2 = np.zeros((cap, 2), np.float32)
+        _check(lib().kd_decoder_result_view(self.h, int(ticket), int(use_final_probs), C.byref(n),
+                                            C.byref(lp), C.byref(wp), C.byref(op), cnt.ctypes.data,
+                                            ok.ctypes.data, rf.ctypes.data, f2.ctypes.data))
+        m = n.value
+        woff = np.ctypeslib.as_array(C.cast(op, C.POINTER(C.c_int64)), shape=(m, 4))
+        n_words = int((woff[:, 3] + cnt[:m]).max()) if m else 0
+        words = (np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_int32)), shape=(n_words,))
+                 if n_words else np.empty(0, np.int32))
+        if copy:
+            words, woff = words.copy(), woff.copy()
+        pb = PathBatch(ok[:m], rf[:m], cnt[:m], words, woff, f2[:m], d2h_bytes=4 * n_words)
+        pb.lanes = np.ctypeslib.as_array(C.cast(lp, C.POINTER(C.c_int32)), shape=(m,)).copy()
+        return pb
+
+    def span_begin(self):
+        _check(lib().kd_decoder_span_begin(self.h))
+
+    def span_end(self) -> Tuple[float, int]:
+        """(device ms from the first launch's start to the last one's end, launches)"""
+        ms = C.c_float(0)
+        nl = C.c_int32(0)
+        _check(lib().kd_decoder_span_end(self.h, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def decode(self, lanes, mats: Sequence[np.ndarray], use_final_probs: bool = True) -> "PathBatch":
+        """InitDecoding + AdvanceDecoding over all rows + GetBestPath of host matrices, one
+        kernel launch."""
+        mats = [np.ascontiguousarray(m, dtype=np.float32) for m in mats]
+        self._keep = mats
+        cols = mats[0].shape[1]
+        t = self.advance_async(lanes, [m.ctypes.data for m in mats], [m.shape[0] for m in mats],
+                               cols, None, -1, KD_MEM_HOST, init=True, finalize=True)
+        self.wait(t)
+        return self.results(t, use_final_probs)
 
     def tokens(self, lane: int) -> Tuple[np.ndarray, np.ndarray]:
         n = C.c_int64(0)

@@ -649,9 +649,10 @@ class Decoder {
     return min_stored + o_.beam;
   }
 
-  // faster-decoder.cc:59-119.  Mode 0 keeps the LIFO worklist; mode 1 sweeps
-  // to the same fixed point (costs are order-independent; on an exact tie the
-  // incumbent stays in both).
+  // faster-decoder.cc:59-119.  Mode 0 keeps the LIFO worklist; modes 1/2 sweep
+  // to the same fixed point (costs are order-independent).  Exact ties: mode 0 keeps the
+  // incumbent; modes 1/2 keep an emitting-phase incumbent, and among epsilon arrivals the
+  // one over the lowest arc index (order-independent, see ExpandEps).
   void Closure(double cutoff) {
     std::vector<int32_t> work;
     map_.ListOrder(&work);
@@ -699,7 +700,23 @@ class Decoder {
         dst.tok = nt;
         push->push_back(cidx);
       } else {
-        if (toks_[dst.tok].cost == nc) stats_.eps_ties++;
+        if (toks_[dst.tok].cost == nc) {
+          stats_.eps_ties++;
+          // Canonical modes: of two epsilon arrivals with bit-equal cost the one over the
+          // lower arc index is the token's backpointer (the reference, mode 0, keeps the
+          // first arrival of its LIFO order, faster-decoder.cc:107-112).  An incumbent
+          // from the emitting phase, or the start token, stays.  The token is rewritten
+          // in place: tokens already expanded from it keep pointing at it, as the CUDA
+          // path's "predecessor = slot of the source state" does.
+          Tok &cur = toks_[dst.tok];
+          if (mode_ != 0 && cur.arc >= 0 && g_->il[cur.arc] == 0 && a < cur.arc) {
+            int32_t old_prev = cur.prev;
+            cur.arc = static_cast<int32_t>(a);
+            cur.prev = t;
+            toks_[t].refs++;
+            Release(old_prev);
+          }
+        }
         Release(nt);
       }
       // `t` may have been freed and reused only if nobody references it; the
