@@ -152,7 +152,7 @@ KD_API int kd_decoder_advance(kd_decoder *d, int32_t n, const int32_t *lanes,
 /* ---- the same call without waiting, and with InitDecoding / GetBestPath folded in.
  *
  * kd_decoder_advance_async enqueues the call and returns; kd_decoder_wait(ticket) completes
- * it and reports its outcome (ticket < 0: every call in flight).  Up to three calls on
+ * it and reports its outcome (ticket < 0: every call in flight).  Up to 16 calls on
  * disjoint lanes are in flight at once, each on its own streams: the upload and the search
  * of one batch of lanes overlap the search and the download of another, and the lanes of
  * the next batch take over the SMs as the slowest lanes of the previous one finish.  Any
@@ -189,7 +189,7 @@ KD_API int kd_decoder_wait(kd_decoder *d, int64_t ticket);
  * *lanes lists the *num_lanes lanes the call advanced, in call order; lane i's arcs are
  * four arrays of num_arcs[i] words -- ilabel, olabel (int32), graph cost, acoustic cost
  * (float) -- starting at (*words)[(*word_offsets)[4 * i + 0..3]].  The pointers address
- * pinned host memory of the decoder and stay valid until the third-next
+ * pinned host memory of the decoder and stay valid until the 16th-next
  * kd_decoder_advance_async call or the decoder's destruction.  ok / reached_final /
  * final_weight2 (2 per lane) as kd_decoder_best_path_prepare / _fetch; any may be NULL,
  * arrays must hold *num_lanes entries (at most the n of the call). */

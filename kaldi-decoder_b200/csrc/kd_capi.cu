@@ -37,7 +37,7 @@ int Fail(int code, const std::string &msg) {
     }                                                                              \
   } while (0)
 
-constexpr int kNumSlots = 3;  // asynchronous calls in flight per decoder
+constexpr int kNumSlots = 16;  // asynchronous calls in flight per decoder
 constexpr int kNumSMsFallback = 148;
 
 template <class T>
@@ -120,7 +120,7 @@ struct kd_decoder {
   int32_t *a_state = nullptr;
   kd::Entry *table = nullptr;
   uint32_t *list = nullptr;
-  uint32_t *queue = nullptr;
+  uint2 *queue = nullptr;
   uint4 *cand = nullptr;
   uint4 *front = nullptr;
   kd::AdvanceItem *d_items = nullptr;  // synchronous helpers (init, best path, ...)
@@ -274,15 +274,22 @@ int LaunchAdvanceSimple(kd_decoder *d, kd::Params P, int n_items, cudaStream_t s
 int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
                   cudaStream_t s) {
   if (d->simple) return LaunchAdvanceSimple(d, P, n_items, s);
+  // (second template argument: lanes per SM the register budget is cut for -- the measured
+  // best per thread count: profiles/r2_sweeps.txt)
+#ifdef KD_ONLY_160
+  // (quick A/B builds: one instantiation)
+  if (threads != 160) return Fail(KD_ERR_INVALID, "this build only has 160-thread lanes");
+  return LaunchAdvanceT<160, 7>(d, P, n_items, s);
+#else
   switch (threads) {
     case 128:
-      return LaunchAdvanceT<128, 7>(d, P, n_items, s);
+      return LaunchAdvanceT<128, 8>(d, P, n_items, s);
     case 160:
       return LaunchAdvanceT<160, 7>(d, P, n_items, s);
     case 192:
       return LaunchAdvanceT<192, 5>(d, P, n_items, s);
     case 224:
-      return LaunchAdvanceT<224, 7>(d, P, n_items, s);
+      return LaunchAdvanceT<224, 5>(d, P, n_items, s);
     case 256:
       return LaunchAdvanceT<256, 4>(d, P, n_items, s);
     case 384:
@@ -290,8 +297,10 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
     case 512:
       return LaunchAdvanceT<512, 1>(d, P, n_items, s);
     default:
-      return Fail(KD_ERR_INVALID, "threads_per_lane must be 128, 160, 192, 224, 256, 384 or 512");
+      return Fail(KD_ERR_INVALID,
+                  "threads_per_lane must be 128, 160, 192, 224, 256, 384 or 512");
   }
+#endif
 }
 
 const char *StatusText(int st) {
@@ -582,7 +591,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
     d->launch_blocking = e != nullptr && e[0] != '\0' && e[0] != '0';
   }
   // Default table size: the largest power of two that keeps all lanes' tables (and their
-  // slot lists, worklists, candidate buffers: 48 bytes per entry) within ~15% of the free
+  // slot lists, worklists, candidate buffers: 54 bytes per entry) within ~15% of the free
   // device memory, between 2^15 and 2^22 entries.  A frame may hold capacity / 2 tokens.
   uint32_t hcap;
   if (c.hash_capacity > 0) {
@@ -590,7 +599,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   } else {
     size_t free_b = 0, total_b = 0;
     KD_CUDA_D(cudaMemGetInfo(&free_b, &total_b));
-    const double per_lane = 0.15 * static_cast<double>(free_b) / d->max_lanes / 48.0;
+    const double per_lane = 0.15 * static_cast<double>(free_b) / d->max_lanes / 56.0;
     hcap = 1u << 15;
     while (hcap < (1u << 22) && 2.0 * hcap <= per_lane) hcap <<= 1;
   }
@@ -607,7 +616,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   const size_t L = static_cast<size_t>(d->max_lanes);
   const size_t table_bytes_per_lane =
       static_cast<size_t>(d->hcap) * sizeof(kd::Entry) + static_cast<size_t>(d->lcap) * 4 +
-      static_cast<size_t>(d->qcap) * 8 + static_cast<size_t>(d->ccap) * 16;
+      static_cast<size_t>(d->qcap) * 16 + static_cast<size_t>(d->ccap) * 16;
   if (c.arena_records > 0) {
     d->arena_cap = c.arena_records;
   } else {
@@ -765,7 +774,7 @@ int EnqueueSearch(kd_decoder *d, kd_slot &s) {
     // the parked paths: lane i's four arrays are 4 * path_cap consecutive words at the head
     // of its worklist buffer.  Consecutive lane ids come back with one 2-D copy.
     const size_t row_bytes = static_cast<size_t>(4) * s.path_cap * sizeof(int32_t);
-    const size_t lane_pitch = static_cast<size_t>(2) * d->qcap * sizeof(uint32_t);
+    const size_t lane_pitch = static_cast<size_t>(2) * d->qcap * sizeof(uint2);
     bool consecutive = lane_pitch <= d->mem_pitch;
     for (int32_t i = 1; i < m && consecutive; ++i)
       if (s.lanes[i] != s.lanes[i - 1] + 1) consecutive = false;

@@ -41,6 +41,20 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Build-time switches of individual optimisations (A/B builds: -DKD_OPT_...=0).
+#ifndef KD_OPT_QSTATE
+#define KD_OPT_QSTATE 1       // epsilon worklist entries carry the state: its record is requested with the entry
+#endif
+#ifndef KD_OPT_GRAPH_EL
+#define KD_OPT_GRAPH_EL 1     // graph loads (state records, label tables, arcs) carry an L2 evict-last policy
+#endif
+#ifndef KD_OPT_SINGLE_PASS
+#define KD_OPT_SINGLE_PASS 1  // token blocks of at most one scan tile are scanned in one pass
+#endif
+#ifndef KD_OPT_SLIST
+#define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
+#endif
+
 namespace kd {
 
 constexpr int kStatusHashOverflow = 1;
@@ -65,6 +79,7 @@ constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the l
 // the scan 5% faster and the other phases slower by as much (code size, registers).
 constexpr int kWin = 1;
 constexpr int kTileTokens = 2;            // tokens per thread in one scan tile
+constexpr int kListSmem = KD_OPT_SLIST ? 1024 : 0;  // slot-list entries kept in shared memory
 constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
@@ -161,7 +176,7 @@ struct Params {
   long long arena_cap;
   Entry *table;
   uint32_t *list;
-  uint32_t *queue;  // 2 * qcap per lane
+  uint2 *queue;     // 2 * qcap per lane: {table slot, state}
   uint4 *cand;      // ccap per lane: arcs that passed the running-cutoff filter
   uint4 *front;     // kFrontCap per lane: {cost, state, number} of the tokens close to the best
   uint32_t hcap, hmask, lcap, qcap, ccap;
@@ -205,12 +220,63 @@ __device__ __forceinline__ float funkey(uint32_t k) {
 // (measured 108.8 -> 103.5 ms per launch).
 __device__ __forceinline__ double widen(float f) { return static_cast<double>(f); }
 
+// L2 eviction policy of the graph.  The recombination tables are scattered over megabytes
+// per lane and every entry is touched a handful of times within one frame; left alone their
+// lines push the graph out of L2 every couple of frames.  Graph loads ask to be evicted last
+// (createpolicy lands in a uniform register).  Measured on the bench workload: 71.6 -> 70.7
+// ms per step.  (The converse -- evict-first on the table's loads and wipes -- is a loss:
+// an entry's probe, CAS, commit read and wipe do find each other in L2, and evict-first
+// makes them miss: recombination 40 k -> 49 k cycles per frame.  ptxas does not take a
+// cache policy on atom.cas.)
+__device__ __forceinline__ unsigned long long l2_evict_last() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// ---- recombination-table accesses
 __device__ __forceinline__ HVal ld_hval(const HVal *p) {
-  ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
   HVal r;
+  ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
   r.cost = v.x;
   r.arg = v.y;
   return r;
+}
+__device__ __forceinline__ int32_t ld_key(const int32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ int2 ld_key_idx(const int32_t *p) {
+  return __ldcg(reinterpret_cast<const int2 *>(p));
+}
+// wipes an entry (value and key)
+__device__ __forceinline__ void st_wipe(Entry *e) {
+  ulonglong2 v;
+  v.x = kEmptyCost;
+  v.y = kEmptyArg;
+  *reinterpret_cast<ulonglong2 *>(&e->val) = v;
+  e->key = kEmptyKey;
+}
+
+// ---- graph loads (read-only path)
+__device__ __forceinline__ int4 gld(const int4 *p) {
+#if KD_OPT_GRAPH_EL
+  int4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(l2_evict_last()));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+__device__ __forceinline__ int2 gld(const int2 *p) {
+#if KD_OPT_GRAPH_EL
+  int2 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.s32 {%0, %1}, [%2], %3;"
+               : "=r"(v.x), "=r"(v.y)
+               : "l"(p), "l"(l2_evict_last()));
+  return v;
+#else
+  return __ldg(p);
+#endif
 }
 
 // 128-bit compare-and-swap (ATOMG.E.CAS.128); returns the previous value.
@@ -397,9 +463,10 @@ struct LaneBuf {
   int32_t *a_state;
   Entry *table;
   uint32_t *list;
-  uint32_t *queue;
+  uint2 *queue;
   uint4 *cand;
   uint4 *front;
+  uint32_t *s_list;  // shared memory: the first kListSmem entries of the slot list
 };
 
 __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
@@ -420,11 +487,15 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
 // token's number in the next block) and, when `eps_queue` is given (the state has
 // epsilon arcs), that queue: the closure only visits those.
 __device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B, Shared &sh,
-                                               uint32_t h, uint32_t *eps_queue,
+                                               uint32_t h, int32_t state, uint2 *eps_queue,
                                                uint32_t *eps_queue_n) {
   const uint32_t pos = atomicAdd(&sh.list_n, 1u);
   if (pos < P.lcap) {
-    B.list[pos] = h;
+    if (pos < static_cast<uint32_t>(kListSmem)) {
+      B.s_list[pos] = h;
+    } else {
+      B.list[pos] = h;
+    }
     B.table[h].idx = pos;  // tokens are numbered in claim order
   } else {
     atomicOr(&sh.status, kStatusHashOverflow);
@@ -432,7 +503,7 @@ __device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B
   if (eps_queue != nullptr) {
     const uint32_t qp = atomicAdd(eps_queue_n, 1u);
     if (qp < P.qcap) {
-      eps_queue[qp] = h;
+      eps_queue[qp] = make_uint2(h, static_cast<uint32_t>(state));
     } else {
       atomicOr(&sh.status, kStatusQueueOverflow);
     }
@@ -448,7 +519,7 @@ __device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B
 // closure only visits those.  Returns kNoIdx on overflow.
 __device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneBuf &B,
                                                     Shared &sh, int32_t state, uint32_t h,
-                                                    int32_t k, uint32_t *eps_queue,
+                                                    int32_t k, uint2 *eps_queue,
                                                     uint32_t *eps_queue_n) {
   // `k` is the key already loaded from slot `h` (the first probe)
   for (uint32_t probe = 0; probe < P.hcap; ++probe) {
@@ -457,12 +528,12 @@ __device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneB
       k = atomicCAS(&B.table[h].key, kEmptyKey, state);
       if (k == state) return h;
       if (k == kEmptyKey) {
-        register_claim(P, B, sh, h, eps_queue, eps_queue_n);
+        register_claim(P, B, sh, h, state, eps_queue, eps_queue_n);
         return h;
       }
     }
     h = (h + 1) & P.hmask;
-    k = __ldcg(&B.table[h].key);
+    k = ld_key(&B.table[h].key);
   }
   atomicOr(&sh.status, kStatusHashOverflow);
   return kNoIdx;
@@ -475,10 +546,10 @@ __device__ __forceinline__ uint32_t table_hash(const Params &P, int32_t state) {
 }
 
 __device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
-                                               int32_t state, uint32_t *eps_queue,
+                                               int32_t state, uint2 *eps_queue,
                                                uint32_t *eps_queue_n) {
   const uint32_t h = table_hash(P, state);
-  return table_slot_from(P, B, sh, state, h, __ldcg(&B.table[h].key), eps_queue, eps_queue_n);
+  return table_slot_from(P, B, sh, state, h, ld_key(&B.table[h].key), eps_queue, eps_queue_n);
 }
 
 // Block-wide count of tokens with float(cost) <= bound (used to skip the exact
@@ -607,12 +678,12 @@ template <bool SIMPLE>
 __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
                                             uint32_t dst_word, unsigned long long cost_key,
                                             uint32_t arc, uint32_t src_number,
-                                            unsigned long long cstar_key, uint32_t *q_next,
+                                            unsigned long long cstar_key, uint2 *q_next,
                                             uint32_t *q_next_n) {
   // key and value of the first probed slot are fetched together (one sector, one round trip)
   const int32_t state = static_cast<int32_t>(dst_word & ~kEpsFlag);
   const uint32_t h0 = table_hash(P, state);
-  const int32_t k0 = __ldcg(&B.table[h0].key);
+  const int32_t k0 = ld_key(&B.table[h0].key);
   HVal cur = ld_hval(&B.table[h0].val);
   uint32_t h = h0;
   if (k0 != state) {
@@ -644,7 +715,7 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
   if (dst_word & kEpsFlag) {
     const uint32_t pos = atomicAdd(q_next_n, 1u);
     if (pos < P.qcap) {
-      q_next[pos] = h;
+      q_next[pos] = make_uint2(h, static_cast<uint32_t>(state));
     } else {
       atomicOr(&sh.status, kStatusQueueOverflow);
     }
@@ -655,21 +726,29 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
 // (faster-decoder.cc:71-117).
 template <bool SIMPLE>
 __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Shared &sh,
-                                           uint32_t slot, unsigned long long cstar_key,
-                                           double cstar, uint32_t *q_next, uint32_t *q_next_n,
+                                           uint2 entry, unsigned long long cstar_key,
+                                           double cstar, uint2 *q_next, uint32_t *q_next_n,
                                            uint32_t *eps_count) {
+  const uint32_t slot = entry.x;
+  // the worklist entry names the state: its record is requested together with the token
+  // (one round trip instead of two)
+#if KD_OPT_QSTATE
+  const int4 st = gld(P.st + 2 * static_cast<size_t>(entry.y));
+#endif
   const HVal v = ld_hval(&B.table[slot].val);
   // {state, number}: same sector as the value, requested together with it
-  const int2 ki = __ldcg(reinterpret_cast<const int2 *>(&B.table[slot].key));
+  const int2 ki = ld_key_idx(&B.table[slot].key);
   const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
   if (v.cost == kEmptyCost || !(SIMPLE || v.cost < cstar_key || is_eps)) return;
-  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(ki.x));
+#if !KD_OPT_QSTATE
+  const int4 st = gld(P.st + 2 * static_cast<size_t>(ki.x));
+#endif
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
   *eps_count += static_cast<uint32_t>(st.w);
   for (int a = st.z; a < st.z + st.w; ++a) {
-    const int4 arc = __ldg(P.n_arc + a);
+    const int4 arc = gld(P.n_arc + a);
     const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
     eps_arrival<SIMPLE>(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a),
@@ -707,7 +786,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   __syncthreads();
   // ---- closure: sweep 0 expands the candidates, later sweeps the improved ones
   uint32_t eps_count = 0;
-  uint32_t *q0 = B.queue, *q1 = B.queue + P.qcap;
+  uint2 *q0 = B.queue, *q1 = B.queue + P.qcap;
   int cur = 0;
   long long sweeps = 0;
   while (true) {
@@ -716,7 +795,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     __syncthreads();
     if (tid == 0) sh.q_n[cur ^ 1] = 0;
     __syncthreads();
-    uint32_t *qc = cur ? q1 : q0, *qx = cur ? q0 : q1;
+    uint2 *qc = cur ? q1 : q0, *qx = cur ? q0 : q1;
     for (uint32_t p = tid; p < qn; p += THREADS)
       expand_eps<SIMPLE>(P, B, sh, qc[p], cstar_key, cstar, qx, &sh.q_n[cur ^ 1], &eps_count);
     __syncthreads();
@@ -747,7 +826,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint32_t p = p0 + u * THREADS + tid;
-      h[u] = p < m ? B.list[p] : kNoIdx;
+      h[u] = p < m ? (p < static_cast<uint32_t>(kListSmem) ? B.s_list[p] : B.list[p]) : kNoIdx;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -756,7 +835,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       key[u] = kEmptyKey;
       if (h[u] != kNoIdx) {
         v[u] = ld_hval(&B.table[h[u]].val);
-        key[u] = __ldcg(&B.table[h[u]].key);
+        key[u] = ld_key(&B.table[h[u]].key);
       }
     }
     // the tokens close to the best also go to the front list (warp-aggregated append)
@@ -802,11 +881,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
           my_state = key[u];
         }
       }
-      ulonglong2 e;
-      e.x = kEmptyCost;
-      e.y = kEmptyArg;
-      *reinterpret_cast<ulonglong2 *>(&B.table[h[u]].val) = e;
-      B.table[h[u]].key = kEmptyKey;
+      st_wipe(&B.table[h[u]]);
     }
   }
   double bmin;
@@ -880,9 +955,9 @@ __device__ __forceinline__ void insert_probed(const Params &P, const LaneBuf &B,
 
 __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
                                            uint32_t a, unsigned long long nk, uint32_t tok_abs) {
-  const int2 no = __ldg(P.e_no + a);
+  const int2 no = gld(P.e_no + a);
   const uint32_t h0 = table_hash(P, no.x & 0x7FFFFFFF);
-  const int32_t k0 = __ldcg(&B.table[h0].key);
+  const int32_t k0 = ld_key(&B.table[h0].key);
   const HVal cur = ld_hval(&B.table[h0].val);  // same sector as the key: one round trip for both
   insert_probed(P, B, sh, a, nk, tok_abs, no, k0, cur);
 }
@@ -946,8 +1021,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // arrives while the row is staged and the labels are ordered
   int4 seed_sa = make_int4(0, 0, 0, 0), seed_sb = make_int4(-1, 0, 0, 0);
   if (n > 0 && ls.best_state >= 0) {
-    seed_sa = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state));
-    seed_sb = __ldg(P.st + 2 * static_cast<size_t>(ls.best_state) + 1);
+    seed_sa = gld(P.st + 2 * static_cast<size_t>(ls.best_state));
+    seed_sb = gld(P.st + 2 * static_cast<size_t>(ls.best_state) + 1);
   }
   // The row is kept as it comes (log-probs); every use negates it (faster-decoder.cc:209).
   // Usually it is already on its way: the previous frame started a bulk copy (TMA) of it
@@ -1060,14 +1135,14 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     if (sh.order_ok != 0 && sb.x >= 0) {
       if (tid < P.cols) {
         const uint32_t lab = lab_order[tid];
-        const int2 ent = __ldg(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
+        const int2 ent = gld(P.labtab + static_cast<size_t>(sb.x) * P.lab_stride + (lab - 1));
         if (ent.y >= 0)
           seed = (widen(__int_as_float(ent.x)) + ls.best_cost) + widen(-s_row[lab - 1]);
       }
     } else {
 #pragma unroll 1
       for (int a = tid; a < st.y; a += THREADS) {
-        const int2 iw = __ldg(P.e_iw + st.x + a);
+        const int2 iw = gld(P.e_iw + st.x + a);
         const double ac = widen(-(ROW_SMEM ? s_row[iw.x - 1] : __ldcg(row_g + iw.x - 1)));
         const double nw = (widen(__int_as_float(iw.y)) + ls.best_cost) + ac;
         seed = fmin(seed, nw);
@@ -1094,14 +1169,17 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // (Loop state is kept in shared memory where it can be: the item loop below needs
   // every register it can get.)
   static_assert(TT <= kFrontCap, "front list smaller than a scan tile");
-  for (int pass = 0; pass < 2; ++pass) {
+  // (a block that fits one tile is scanned in one pass: the second pass would cost three
+  // more dependent round trips and has little left to tighten)
+  const bool single_pass = KD_OPT_SINGLE_PASS && ls.n_tok <= TT;
+  for (int pass = single_pass ? 1 : 0; pass < 2; ++pass) {
     // pass 0 reads the front list the commit wrote, unless it overflowed (then it filters the block)
     const bool front_list =
         pass == 0 && static_cast<uint32_t>(ls.n_front) <= static_cast<uint32_t>(kFrontCap);
     const uint32_t un = static_cast<uint32_t>(front_list ? ls.n_front : ls.n_tok);
     for (uint32_t tile0 = 0; tile0 < un; tile0 += TT) {
     const double wcut = sh.wc;
-    const double good = fmin(ls.good_cut, wcut);
+    const double good = single_pass ? -inf : fmin(ls.good_cut, wcut);
     const uint32_t tile_end = min(un, tile0 + TT);
     // chunk setup: 4 consecutive tokens per thread -> (cost, arc range or label
     // count) of the tokens to expand
@@ -1137,8 +1215,8 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         sa[k] = make_int4(0, 0, 0, 0);
         sb[k] = make_int4(-1, 0, 0, 0);
         if (ts[k] >= 0) {
-          sa[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]));
-          sb[k] = __ldg(P.st + 2 * static_cast<size_t>(ts[k]) + 1);
+          sa[k] = gld(P.st + 2 * static_cast<size_t>(ts[k]));
+          sb[k] = gld(P.st + 2 * static_cast<size_t>(ts[k]) + 1);
         }
       }
       // a valid bound on this frame's final cutoff (the seeded running cutoff)
@@ -1262,7 +1340,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
               // one load gives the arc's weight and its offset within the state
               const uint32_t lab = lab_order[k];
               const int2 ent =
-                  __ldg(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
+                  gld(P.labtab + static_cast<size_t>(t_tab[t]) * P.lab_stride + (lab - 1));
               if (ent.y >= 0) {  // else: the state has no arc with this label
                 tt[u] = t;
                 aa[u] = (b & ~kLookupFlag) + static_cast<uint32_t>(ent.y);
@@ -1271,7 +1349,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
             } else {
               tt[u] = t;
               aa[u] = b + k;
-              iw[u] = __ldg(P.e_iw + aa[u]);
+              iw[u] = gld(P.e_iw + aa[u]);
             }
           }
         }
@@ -1343,7 +1421,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     if (SIMPLE) {
       // SimpleDecoder prunes on (cost + w) + ac but stores cost + float(w + ac)
       // (simple-decoder.cc:168 vs simple-decoder.h:96)
-      const int2 iw = __ldg(P.e_iw + c.z);
+      const int2 iw = gld(P.e_iw + c.z);
       const float ac = -(ROW_SMEM ? s_row[iw.x - 1] : __ldcg(row_g + iw.x - 1));
       const double stored = B.a_cost[c.w] + static_cast<double>(__fadd_rn(__int_as_float(iw.y), ac));
       min_stored = fmin(min_stored, stored);
@@ -1394,7 +1472,7 @@ constexpr int advance_max_regs(int threads, int min_blocks) {
 // The start token (faster-decoder.cc:46-52): cost 0 at Start(), no arc, no predecessor.
 // One thread; the caller closes it over the epsilon arcs and commits.
 __device__ __forceinline__ void lane_start_token(const Params &P, const LaneBuf &B, Shared &sh) {
-  const int4 st = __ldg(P.st + 2 * static_cast<size_t>(P.start));
+  const int4 st = gld(P.st + 2 * static_cast<size_t>(P.start));
   const uint32_t h = table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
   if (h == kNoIdx) return;
   HVal v;
@@ -1421,13 +1499,13 @@ __device__ __forceinline__ void write_path_arc(const Params &P, uint32_t arc, do
   int32_t ilab, olab;
   float graph;
   if (arc & kEpsFlag) {
-    const int4 a = __ldg(P.n_arc + (arc & ~kEpsFlag));
+    const int4 a = gld(P.n_arc + (arc & ~kEpsFlag));
     ilab = 0;
     olab = a.x;
     graph = __int_as_float(a.y);
   } else {
-    const int2 iw = __ldg(P.e_iw + arc);
-    const int2 no = __ldg(P.e_no + arc);
+    const int2 iw = gld(P.e_iw + arc);
+    const int2 no = gld(P.e_no + arc);
     ilab = iw.x;
     olab = no.y;
     graph = __int_as_float(iw.y);
@@ -1610,6 +1688,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
   __shared__ Shared sh;
   __shared__ LaneState ls;
   __shared__ LaneBuf sB;  // per-lane base pointers live in shared memory, not registers
+  __shared__ uint32_t s_list[kListSmem > 0 ? kListSmem : 1];
   const LaneBuf &B = sB;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   double *t_cost = reinterpret_cast<double *>(dyn_smem);
@@ -1640,6 +1719,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
     bool init_pass = (it.flags & kItemInit) != 0;
     if (tid == 0) {
       sB = lane_buffers(P, it.lane);
+      sB.s_list = s_list;
       if (init_pass) {
         lane_state_reset(ls);
       } else {
@@ -1747,7 +1827,9 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
   const int item = blockIdx.x;
   if (item >= P.n_items) return;
   const int lane = P.items[item].lane;
-  const LaneBuf B = lane_buffers(P, lane);
+  __shared__ uint32_t s_list[kListSmem > 0 ? kListSmem : 1];
+  LaneBuf B = lane_buffers(P, lane);
+  B.s_list = s_list;
   if (tid == 0) {
     lane_state_reset(ls);
     sh.status = 0;

@@ -40,3 +40,12 @@ for j, nme in enumerate(names):
 for j, nme in ((7, "arcs_evaluated"), (8, "candidates")):
     y = a[:, j] / T
     print("%-15s mean %8.0f | heaviest 5%%: %8.0f" % (nme, y.mean(), y[heavy].mean()))
+rec = (a[:, 1] - a[:, 4]) / T
+b, c = np.polyfit(x, rec, 1)
+print("recombine       mean %8.0f  = %8.0f + %6.1f * tokens   | heaviest 5%%: %8.0f" % (rec.mean(), c, b, rec[heavy].mean()))
+print("slowest lanes: (busy ms, tokens/frame, recomb cyc/frame, cand/frame)")
+for u in order[-6:]:
+    print("  lane %4d  %.1f ms  %6.0f tok  %8.0f  %6.0f" % (u, tot[u], x[u], rec[u], a[u, 8] / T))
+print("fastest lanes:")
+for u in order[:3]:
+    print("  lane %4d  %.1f ms  %6.0f tok  %8.0f  %6.0f" % (u, tot[u], x[u], rec[u], a[u, 8] / T))
