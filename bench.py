@@ -117,6 +117,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """The timed region starts here: earlier samples are dropped."""
+        self.first = len(self.lines)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -126,7 +130,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -327,9 +331,12 @@ def main():
     # one launch alone (nothing else on the GPU): its CUDA-event duration
     run_steps(dptrs, capi.KD_MEM_DEVICE, 1)
     single_ms = dec.last_advance_info()[0]
+    # (nvidia-smi is started before the warm-up: its start-up holds the driver for tens of ms;
+    # only the samples taken during the timed region are kept)
     sampler = ClockSampler(local_rank)
-    timed(dptrs, capi.KD_MEM_DEVICE, 0, args.warmup)
     sampler.start()
+    timed(dptrs, capi.KD_MEM_DEVICE, 0, args.warmup)
+    sampler.mark()
     dt, span_ms, n_launch = timed(dptrs, capi.KD_MEM_DEVICE, args.steps, 0)
     clocks = sampler.stop()
     st = dec.stats()  # counters of the last step of every lane group (InitDecoding resets them)

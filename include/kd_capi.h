@@ -103,6 +103,8 @@ typedef struct kd_stats {
   int64_t arcs_evaluated;  /* arcs actually loaded: scanned, or found through a label
                               table; emit_arcs - this = arcs skipped as provably pruned */
   int64_t cycles_scan;     /* part of cycles_expand before the exact cutoff       */
+  int64_t arena_compactions; /* garbage collections of the backpointer arena (a lane's records
+                              are compacted when a frame's tokens no longer fit)   */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

@@ -1637,6 +1637,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->candidates += L.st_cand;
     out->arcs_evaluated += L.st_items;
     out->cycles_scan += L.cyc_scan;
+    out->arena_compactions += L.st_compactions;
   }
   return KD_OK;
 }

@@ -120,6 +120,7 @@ struct __align__(16) LaneState {
   // SM cycles spent per phase (clock64 of thread 0), for the phase breakdown
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit, cyc_scan;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
+  long long st_compactions;  // arena garbage collections
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
   long long st_items;    // arcs actually evaluated (scanned + looked up)
   // best-path selection results
@@ -756,6 +757,118 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   }
 }
 
+// Garbage collection of the backpointer arena (the reference frees a token when the last
+// token pointing at it dies, faster-decoder.h:145-155, so its memory follows the live
+// history; here the arena is compacted when a frame's tokens no longer fit).  The records
+// below `tok_base` are kept iff a token of the current block reaches them:
+//   1. mark   every token of the block walks its backpointers until it meets a marked record
+//             (marks live in a_state of the old records, which nothing reads any more);
+//   2. scan   marked records get their new, order-preserving index (left in a_state);
+//   3. move   old records slide down tile by tile (all reads of a tile before its writes;
+//             targets never lie above their sources), links rewritten through the new indices;
+//   4. block  the current block's links are rewritten in place, then it slides down behind
+//             the kept records.
+// Returns how far the current block moved (the caller still holds its old indices).  Cold
+// path: once per several thousand frames of a long stream.
+template <int THREADS>
+__device__ __noinline__ uint32_t lane_compact_arena(const LaneBuf &B, Shared &sh, LaneState &ls) {
+  constexpr int32_t kMark = -2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = THREADS / 32;
+  const uint32_t base = ls.tok_base;
+  const uint32_t n = static_cast<uint32_t>(ls.n_tok);
+  // ---- 1. mark
+  for (uint32_t i = tid; i < n; i += THREADS) {
+    uint32_t p = static_cast<uint32_t>(B.a_link[base + i]);
+    while (p != kNoPrev && p < base) {
+      if (atomicExch(&B.a_state[p], kMark) == kMark) break;
+      p = static_cast<uint32_t>(B.a_link[p]);
+    }
+  }
+  __syncthreads();
+  // ---- 2. scan: a_state[i] = new index of a marked record, -1 otherwise
+  uint32_t running = 0;  // kept records below the current tile (uniform)
+  for (uint32_t t0 = 0; t0 < base; t0 += THREADS) {
+    const uint32_t i = t0 + tid;
+    const uint32_t keep = (i < base && B.a_state[i] == kMark) ? 1u : 0u;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep != 0);
+    if (lane == 0) sh.warp_sums[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t ex = running + __popc(bal & ((1u << lane) - 1u));
+    uint32_t tile = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const uint32_t c = sh.warp_sums[w];
+      if (w < warp) ex += c;
+      tile += c;
+    }
+    if (i < base) B.a_state[i] = keep ? static_cast<int32_t>(ex) : -1;
+    running += tile;
+    __syncthreads();
+  }
+  const uint32_t kept = running;
+  // ---- 3. move the kept old records
+  for (uint32_t t0 = 0; t0 < base; t0 += THREADS) {
+    const uint32_t i = t0 + tid;
+    int32_t dst = -1;
+    double c = 0.0;
+    unsigned long long link = 0;
+    if (i < base) {
+      dst = B.a_state[i];
+      if (dst >= 0) {
+        c = B.a_cost[i];
+        link = B.a_link[i];
+        const uint32_t p = static_cast<uint32_t>(link);
+        if (p != kNoPrev)
+          link = (link & 0xFFFFFFFF00000000ull) | static_cast<uint32_t>(B.a_state[p]);
+      }
+    }
+    __syncthreads();
+    if (dst >= 0) {
+      B.a_cost[dst] = c;
+      B.a_link[dst] = link;
+    }
+    __syncthreads();
+  }
+  // ---- 4. the current block: links in place, then down to `kept`
+  for (uint32_t i = tid; i < n; i += THREADS) {
+    unsigned long long link = B.a_link[base + i];
+    const uint32_t p = static_cast<uint32_t>(link);
+    if (p != kNoPrev) {
+      const uint32_t np = p >= base ? p - base + kept : static_cast<uint32_t>(B.a_state[p]);
+      B.a_link[base + i] = (link & 0xFFFFFFFF00000000ull) | np;
+    }
+  }
+  __syncthreads();
+  if (kept < base) {
+    for (uint32_t t0 = 0; t0 < n; t0 += THREADS) {
+      const uint32_t i = t0 + tid;
+      double c = 0.0;
+      unsigned long long link = 0;
+      int32_t st = -1;
+      if (i < n) {
+        c = B.a_cost[base + i];
+        link = B.a_link[base + i];
+        st = B.a_state[base + i];
+      }
+      __syncthreads();
+      if (i < n) {
+        B.a_cost[kept + i] = c;
+        B.a_link[kept + i] = link;
+        B.a_state[kept + i] = st;
+      }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    ls.tok_base = kept;
+    ls.arena_used = kept + n;
+    ls.st_compactions += 1;
+  }
+  __syncthreads();
+  return base - kept;
+}
+
 // Epsilon closure (faster-decoder.cc:59-119) followed by the commit of the
 // frame: live table entries become the next token block in the arena, the
 // table is wiped, and the block's min cost is recorded for the next GetCutoff.
@@ -809,6 +922,12 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   // an epsilon arrival carries is final and nothing has to be counted first.  A
   // thread wipes (key, val) of its own entries after reading them.
   const uint32_t m = min(sh.list_n, P.lcap);
+  // The block does not fit behind the records in use: drop the records no live token
+  // reaches any more.  The table's emitting arrivals still name their predecessors by the
+  // old indices of the current block, which moved down by `moved`.
+  uint32_t moved = 0;
+  if (static_cast<long long>(ls.arena_used) + m > P.arena_cap && ls.tok_base > 0)
+    moved = lane_compact_arena<THREADS>(B, sh, ls);
   const uint32_t new_base = ls.arena_used;
   if (static_cast<long long>(new_base) + m > P.arena_cap) {
     if (tid == 0) sh.status |= kStatusArenaOverflow;
@@ -869,7 +988,11 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       if (write_ok) {
         const uint32_t arc = static_cast<uint32_t>(v[u].arg >> 32);
         uint32_t prev = static_cast<uint32_t>(v[u].arg);
-        if (arc & kEpsFlag) prev += new_base;  // predecessor is a token of this block
+        if (arc & kEpsFlag) {
+          prev += new_base;  // predecessor is a token of this block
+        } else if (arc != kNoArc) {
+          prev -= moved;     // predecessor is a token of the previous block
+        }
         const double c = live ? dunkey(v[u].cost) : inf;
         // written once, read once next frame (cost, state) or at traceback (link)
         __stcs(B.a_cost + new_base + idx, c);

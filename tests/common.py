@@ -86,3 +86,46 @@ class GoldenCase:
 
     def reached_final(self, u):
         return bool(self.z[f"reached_final{u}"])
+
+
+def parity_table(g, mats, opts, gpu_paths, threads=None):
+    """SURVEY.md section 8(d) parity protocol for one batch: the device's best paths
+    (`gpu_paths[u]`: RawPath) against the compiled reference (oracle/_ref).  Every utterance
+    is classified identical / exact tie / real (label sequences differ; a tie if the total
+    costs agree to 1e-6 relative, the float32 rounding of the summed path weights), split by
+    whether GetCutoff ever returned through max_active on it (the reference's pruning is
+    order dependent from the first such frame on)."""
+    import os
+    threads = threads or len(os.sched_getaffinity(0))
+    mats = np.ascontiguousarray(np.stack(mats), dtype=np.float32)
+    ropts = kd_ref.Options(**opts)
+    _, rpaths, rrf = kd_ref.decode_batch(kd_ref.RefGraph(g), mats, ropts, threads, want_paths=True)
+    _, _, _, _, per = kd_oracle.decode_batch(kd_oracle.OracleGraph(g), mats, ropts, threads,
+                                             mode=kd_oracle.REFERENCE_ORDER, want_paths=False)
+    names = list(kd_oracle.STAT_NAMES)
+    bmax = per[:, names.index("binding_max")]
+    out = {"utterances": len(mats), "identical": 0,
+           "max_active_binding_utts": int((bmax > 0).sum()),
+           "max_active_binding_frames": int(bmax.sum()),
+           "min_active_binding_frames": int(per[:, names.index("binding_min")].sum()),
+           "never_binding": {"utts": 0, "identical": 0, "ties": 0, "real": 0},
+           "binding": {"utts": 0, "identical": 0, "ties": 0, "real": 0},
+           "max_rel_cost_diff": 0.0, "reached_final_mismatch": 0, "ok_mismatch": 0}
+    for u in range(len(mats)):
+        cls = out["binding" if bmax[u] > 0 else "never_binding"]
+        cls["utts"] += 1
+        p, r = gpu_paths[u], rpaths[u]
+        if p.ok != r.ok:
+            out["ok_mismatch"] += 1
+        if bool(p.reached_final) != bool(rrf[u]):
+            out["reached_final_mismatch"] += 1
+        rel = abs(p.total_cost - r.total_cost) / max(1.0, abs(r.total_cost)) if r.ok and p.ok else 0.0
+        out["max_rel_cost_diff"] = max(out["max_rel_cost_diff"], rel)
+        if np.array_equal(p.isyms, r.isyms) and np.array_equal(p.osyms, r.osyms):
+            cls["identical"] += 1
+            out["identical"] += 1
+        elif rel <= 1e-6:
+            cls["ties"] += 1
+        else:
+            cls["real"] += 1
+    return out
