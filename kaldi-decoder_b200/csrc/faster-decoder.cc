@@ -69,18 +69,19 @@ void BuildLattice(int64_t n, const int32_t *il, const int32_t *ol, const float *
 // --------------------------------------------------------------- DeviceGraph
 
 DeviceGraph::DeviceGraph(const fst::Fst<fst::StdArc> &fst, int32_t device) : device_(device) {
-  const int32_t n = fst.NumStates();
+  // Only what OpenFst's abstract Fst<Arc> offers: CountStates, Start, Final, ArcIterator
+  // (NumStates() lives on ExpandedFst; the reference binds `const Fst<StdArc>&`).
+  const int32_t n = fst::CountStates(fst);
   std::vector<int64_t> off(static_cast<size_t>(std::max(n, 0)) + 1, 0);
   std::vector<int32_t> il, ol, ns;
   std::vector<float> w, fin(static_cast<size_t>(std::max(n, 0)));
   for (int32_t s = 0; s < n; ++s) {
-    fst::ArcIteratorData<fst::StdArc> d;
-    fst.InitArcIterator(s, &d);
-    for (size_t i = 0; i < d.narcs; ++i) {
-      il.push_back(d.arcs[i].ilabel);
-      ol.push_back(d.arcs[i].olabel);
-      w.push_back(d.arcs[i].weight.Value());
-      ns.push_back(d.arcs[i].nextstate);
+    for (fst::ArcIterator<fst::Fst<fst::StdArc>> aiter(fst, s); !aiter.Done(); aiter.Next()) {
+      const fst::StdArc &arc = aiter.Value();
+      il.push_back(arc.ilabel);
+      ol.push_back(arc.olabel);
+      w.push_back(arc.weight.Value());
+      ns.push_back(arc.nextstate);
     }
     off[s + 1] = static_cast<int64_t>(il.size());
     fin[s] = fst.Final(s).Value();
@@ -127,6 +128,21 @@ void FasterDecoder::InitDecoding() {
 }
 
 void FasterDecoder::Decode(DecodableInterface *decodable) {
+  // DecodableCtc: InitDecoding, every ready frame and the best-path selection that
+  // ReachedFinal() / GetBestPath() will ask for, in ONE kernel launch.
+  if (auto *ctc = dynamic_cast<DecodableCtc *>(decodable)) {
+    if (ctc->Offset() == 0) {
+      const int32_t lane = 0;
+      const float *p = ctc->Data();
+      const int32_t rows = ctc->NumRows();
+      int64_t ticket = -1;
+      Check(kd_decoder_advance_async(impl_->dec, 1, &lane, &p, &rows, ctc->NumCols(), nullptr, -1,
+                                     KD_MEM_HOST, KD_ADVANCE_INIT | KD_ADVANCE_FINALIZE, nullptr,
+                                     &ticket));
+      Check(kd_decoder_wait(impl_->dec, ticket));
+      return;
+    }
+  }
   InitDecoding();
   AdvanceDecoding(decodable);
 }
@@ -246,8 +262,45 @@ void BatchFasterDecoder::Decode(const std::vector<int32_t> &lanes,
                                 const std::vector<const float *> &mats,
                                 const std::vector<int32_t> &rows, int32_t cols,
                                 bool device_memory) {
-  InitDecoding(lanes);
-  AdvanceDecoding(lanes, mats, rows, cols, {}, -1, device_memory);
+  Wait(DecodeAsync(lanes, mats, rows, cols, device_memory));
+}
+
+int64_t BatchFasterDecoder::DecodeAsync(const std::vector<int32_t> &lanes,
+                                        const std::vector<const float *> &mats,
+                                        const std::vector<int32_t> &rows, int32_t cols,
+                                        bool device_memory, void *producer_stream) {
+  KALDI_DECODER_ASSERT(mats.size() == lanes.size() && rows.size() == lanes.size());
+  int64_t ticket = -1;
+  Check(kd_decoder_advance_async(impl_->dec, static_cast<int32_t>(lanes.size()), lanes.data(),
+                                 mats.data(), rows.data(), cols, nullptr, -1,
+                                 device_memory ? KD_MEM_DEVICE : KD_MEM_HOST,
+                                 KD_ADVANCE_INIT | KD_ADVANCE_FINALIZE, producer_stream, &ticket));
+  return ticket;
+}
+
+void BatchFasterDecoder::Wait(int64_t ticket) { Check(kd_decoder_wait(impl_->dec, ticket)); }
+
+void BatchFasterDecoder::GetResults(int64_t ticket, std::vector<int32_t> *lanes,
+                                    std::vector<fst::Lattice> *out, std::vector<bool> *ok,
+                                    bool use_final_probs) {
+  int32_t n = 0;
+  const int32_t *lane_ids = nullptr, *words = nullptr;
+  const int64_t *woff = nullptr;
+  std::vector<int64_t> cnt(impl_->max_lanes);
+  std::vector<int32_t> okv(impl_->max_lanes), rf(impl_->max_lanes);
+  std::vector<float> f2(2 * static_cast<size_t>(impl_->max_lanes));
+  Check(kd_decoder_result_view(impl_->dec, ticket, use_final_probs ? 1 : 0, &n, &lane_ids, &words,
+                               &woff, cnt.data(), okv.data(), rf.data(), f2.data()));
+  if (lanes) lanes->assign(lane_ids, lane_ids + n);
+  out->assign(n, fst::Lattice());
+  ok->assign(n, false);
+  for (int32_t i = 0; i < n; ++i) {
+    if (!okv[i]) continue;
+    (*ok)[i] = true;
+    BuildLattice(cnt[i], words + woff[4 * i], words + woff[4 * i + 1],
+                 reinterpret_cast<const float *>(words + woff[4 * i + 2]),
+                 reinterpret_cast<const float *>(words + woff[4 * i + 3]), &f2[2 * i], &(*out)[i]);
+  }
 }
 
 int32_t BatchFasterDecoder::NumFramesDecoded(int32_t lane) const {
@@ -275,9 +328,8 @@ bool BatchFasterDecoder::GetBestPath(int32_t lane, fst::MutableFst<fst::LatticeA
   if (l.Start() != fst::kNoStateId) fst_out->SetStart(l.Start());
   for (int s = 0; s < l.NumStates(); ++s) {
     fst_out->SetFinal(s, l.Final(s));
-    fst::ArcIteratorData<fst::LatticeArc> d;
-    l.InitArcIterator(s, &d);
-    for (size_t i = 0; i < d.narcs; ++i) fst_out->AddArc(s, d.arcs[i]);
+    for (fst::ArcIterator<fst::Lattice> aiter(l, s); !aiter.Done(); aiter.Next())
+      fst_out->AddArc(s, aiter.Value());
   }
   return true;
 }

@@ -144,9 +144,21 @@ class BatchFasterDecoder {
                        const std::vector<int32_t> &rows, int32_t cols,
                        const std::vector<int32_t> &offsets = {}, int32_t max_num_frames = -1,
                        bool device_memory = false);
-  // InitDecoding + AdvanceDecoding over all frames.
+  // InitDecoding + AdvanceDecoding over all frames (+ the best-path selection): one launch.
   void Decode(const std::vector<int32_t> &lanes, const std::vector<const float *> &mats,
               const std::vector<int32_t> &rows, int32_t cols, bool device_memory = false);
+  // The same, deferred: returns a ticket at once.  Several calls on disjoint lanes may be in
+  // flight (the upload and search of one batch overlap the search and download of another);
+  // any other method that touches a lane completes the call that owns it first.  Host
+  // matrices must stay valid until then.  producer_stream (device matrices): the
+  // cudaStream_t the matrices were produced on (nullptr: the legacy default stream).
+  int64_t DecodeAsync(const std::vector<int32_t> &lanes, const std::vector<const float *> &mats,
+                      const std::vector<int32_t> &rows, int32_t cols, bool device_memory = false,
+                      void *producer_stream = nullptr);
+  void Wait(int64_t ticket);
+  // Best paths of a DecodeAsync call, in call order, without any further kernel.
+  void GetResults(int64_t ticket, std::vector<int32_t> *lanes, std::vector<fst::Lattice> *out,
+                  std::vector<bool> *ok, bool use_final_probs = true);
   int32_t NumFramesDecoded(int32_t lane) const;
   bool ReachedFinal(int32_t lane) const;
   bool GetBestPath(int32_t lane, fst::MutableFst<fst::LatticeArc> *fst_out,

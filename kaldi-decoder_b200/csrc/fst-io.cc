@@ -41,6 +41,23 @@ void WriteString(std::ostream &os, const std::string &s) {
   os.write(s.data(), static_cast<std::streamsize>(s.size()));
 }
 
+// OpenFst SymbolTable binary form (symbol-table.cc, SymbolTableImpl::Read): magic int32,
+// name string, available_key int64, size int64, then size x {symbol string, key int64}.
+constexpr int32_t kSymbolTableMagic = 2125658996;
+
+void SkipSymbolTable(std::istream &is) {
+  if (ReadPod<int32_t>(is) != kSymbolTableMagic)
+    KALDI_DECODER_ERR << "bad symbol table in FST file";
+  (void)ReadString(is);          // name
+  (void)ReadPod<int64_t>(is);    // available_key
+  const int64_t size = ReadPod<int64_t>(is);
+  if (size < 0) KALDI_DECODER_ERR << "bad symbol table size in FST file";
+  for (int64_t i = 0; i < size; ++i) {
+    (void)ReadString(is);
+    (void)ReadPod<int64_t>(is);
+  }
+}
+
 void AlignInput(std::istream &is, int64_t align = 16) {
   int64_t pos = static_cast<int64_t>(is.tellg());
   if (pos < 0) return;
@@ -61,8 +78,10 @@ fst::StdVectorFst ReadFstBinary(std::istream &is) {
   const int64_t num_states = ReadPod<int64_t>(is);
   const int64_t num_arcs = ReadPod<int64_t>(is);
   if (arc_type != "standard") KALDI_DECODER_ERR << "unsupported arc type: " << arc_type;
-  if (flags & (kFlagHasIsyms | kFlagHasOsyms))
-    KALDI_DECODER_ERR << "FST files with embedded symbol tables are not supported";
+  // Embedded symbol tables follow the header (OpenFst FstImpl::ReadHeader); the decoder works
+  // on integer labels, so they are skipped.
+  if (flags & kFlagHasIsyms) SkipSymbolTable(is);
+  if (flags & kFlagHasOsyms) SkipSymbolTable(is);
   fst::StdVectorFst out;
   if (fst_type == "vector") {
     out.ReserveStates(static_cast<size_t>(std::max<int64_t>(num_states, 0)));
@@ -128,7 +147,7 @@ fst::StdVectorFst ReadFst(const std::string &path) {
 }
 
 void WriteFstBinary(const fst::Fst<fst::StdArc> &fst, std::ostream &os) {
-  const int32_t n = fst.NumStates();
+  const int32_t n = fst::CountStates(fst);
   int64_t num_arcs = 0;
   for (int32_t s = 0; s < n; ++s) num_arcs += static_cast<int64_t>(fst.NumArcs(s));
   WritePod<int32_t>(os, kFstMagic);
@@ -142,14 +161,13 @@ void WriteFstBinary(const fst::Fst<fst::StdArc> &fst, std::ostream &os) {
   WritePod<int64_t>(os, num_arcs);
   for (int32_t s = 0; s < n; ++s) {
     WritePod<float>(os, fst.Final(s).Value());
-    fst::ArcIteratorData<fst::StdArc> d;
-    fst.InitArcIterator(s, &d);
-    WritePod<int64_t>(os, static_cast<int64_t>(d.narcs));
-    for (size_t a = 0; a < d.narcs; ++a) {
-      WritePod<int32_t>(os, d.arcs[a].ilabel);
-      WritePod<int32_t>(os, d.arcs[a].olabel);
-      WritePod<float>(os, d.arcs[a].weight.Value());
-      WritePod<int32_t>(os, d.arcs[a].nextstate);
+    WritePod<int64_t>(os, static_cast<int64_t>(fst.NumArcs(s)));
+    for (fst::ArcIterator<fst::Fst<fst::StdArc>> aiter(fst, s); !aiter.Done(); aiter.Next()) {
+      const fst::StdArc &arc = aiter.Value();
+      WritePod<int32_t>(os, arc.ilabel);
+      WritePod<int32_t>(os, arc.olabel);
+      WritePod<float>(os, arc.weight.Value());
+      WritePod<int32_t>(os, arc.nextstate);
     }
   }
 }
@@ -210,13 +228,12 @@ fst::StdVectorFst ReadFstText(const std::string &text, bool acceptor) {
 std::string WriteFstText(const fst::Fst<fst::StdArc> &fst) {
   std::ostringstream os;
   os.precision(9);
-  const int32_t n = fst.NumStates();
+  const int32_t n = fst::CountStates(fst);
   auto dump = [&](int32_t s) {
-    fst::ArcIteratorData<fst::StdArc> d;
-    fst.InitArcIterator(s, &d);
-    for (size_t a = 0; a < d.narcs; ++a) {
-      os << s << " " << d.arcs[a].nextstate << " " << d.arcs[a].ilabel << " " << d.arcs[a].olabel;
-      if (d.arcs[a].weight.Value() != 0.0f) os << " " << d.arcs[a].weight.Value();
+    for (fst::ArcIterator<fst::Fst<fst::StdArc>> aiter(fst, s); !aiter.Done(); aiter.Next()) {
+      const fst::StdArc &arc = aiter.Value();
+      os << s << " " << arc.nextstate << " " << arc.ilabel << " " << arc.olabel;
+      if (arc.weight.Value() != 0.0f) os << " " << arc.weight.Value();
       os << "\n";
     }
     if (fst.Final(s) != fst::TropicalWeight::Zero()) {
@@ -242,7 +259,7 @@ bool GetLinearSymbolSequence(const fst::Fst<fst::LatticeArc> &fst, std::vector<i
     if (total) *total = fst::LatticeWeight::Zero();
     return false;
   }
-  const int n = fst.NumStates();
+  const int n = fst::CountStates(fst);
   for (int steps = 0; steps <= n; ++steps) {
     const fst::LatticeWeight fin = fst.Final(s);
     const size_t narcs = fst.NumArcs(s);
@@ -253,9 +270,8 @@ bool GetLinearSymbolSequence(const fst::Fst<fst::LatticeArc> &fst, std::vector<i
       return true;
     }
     if (narcs != 1) return false;
-    fst::ArcIteratorData<fst::LatticeArc> d;
-    fst.InitArcIterator(s, &d);
-    const fst::LatticeArc &a = d.arcs[0];
+    fst::ArcIterator<fst::Fst<fst::LatticeArc>> aiter(fst, s);
+    const fst::LatticeArc &a = aiter.Value();
     tot = fst::Times(tot, a.weight);
     if (a.ilabel != 0 && isyms) isyms->push_back(a.ilabel);
     if (a.olabel != 0 && osyms) osyms->push_back(a.olabel);

@@ -9,8 +9,9 @@
 //   fst::kNoStateId, fst::kNoLabel
 //   fst::TropicalWeightTpl<float>  {Value, One, Zero, ==, !=}
 //   fst::ArcTpl<W>, fst::StdArc    {ilabel, olabel, weight, nextstate}
-//   fst::Fst<A>                    {Start, Final, NumArcs, InitArcIterator}
-//   fst::ExpandedFst<A>            {NumStates}
+//   fst::Fst<A>                    {Start, Final, NumArcs, InitStateIterator, InitArcIterator}
+//   fst::ExpandedFst<A>            {NumStates}   (as in OpenFst, NOT on Fst<A>)
+//   fst::CountStates(const Fst<A>&)
 //   fst::MutableFst<A>             {DeleteStates, AddState, SetStart, AddArc,
 //                                   SetFinal}
 //   fst::VectorFst<A>, fst::ConstFst<A>
@@ -120,6 +121,12 @@ struct ArcIteratorData {
   size_t narcs = 0;
 };
 
+// What a StateIterator needs (every minifst type numbers its states 0..nstates-1).
+template <class A>
+struct StateIteratorData {
+  typename A::StateId nstates = 0;
+};
+
 // Abstract read-only FST.
 template <class A>
 class Fst {
@@ -133,14 +140,22 @@ class Fst {
   virtual StateId Start() const = 0;
   virtual Weight Final(StateId s) const = 0;
   virtual size_t NumArcs(StateId s) const = 0;
+  virtual void InitStateIterator(StateIteratorData<A> *data) const = 0;
   virtual void InitArcIterator(StateId s, ArcIteratorData<A> *data) const = 0;
-  // Number of states; every concrete type in minifst is "expanded".
-  virtual StateId NumStates() const = 0;
   virtual const std::string &Type() const = 0;
 };
 
+// An FST whose states can be counted without walking them.  As in OpenFst, NumStates() is
+// NOT part of Fst<A>: code that only has a `const Fst<A>&` uses StateIterator / CountStates.
 template <class A>
-class ExpandedFst : public Fst<A> {};
+class ExpandedFst : public Fst<A> {
+ public:
+  using StateId = typename A::StateId;
+  virtual StateId NumStates() const = 0;
+  void InitStateIterator(StateIteratorData<A> *data) const override {
+    data->nstates = NumStates();
+  }
+};
 
 template <class A>
 class MutableFst : public ExpandedFst<A> {
@@ -247,7 +262,9 @@ class VectorFst : public MutableFst<A> {
   };
 
   void CopyFrom(const Fst<A> &other) {
-    StateId n = other.NumStates();
+    StateIteratorData<A> sd;
+    other.InitStateIterator(&sd);
+    StateId n = sd.nstates;
     states_.resize(n);
     start_ = other.Start();
     for (StateId s = 0; s < n; ++s) {
@@ -274,7 +291,9 @@ class ConstFst : public ExpandedFst<A> {
   ConstFst() : offsets_(1, 0) {}
 
   explicit ConstFst(const Fst<A> &other) {
-    StateId n = other.NumStates();
+    StateIteratorData<A> sd;
+    other.InitStateIterator(&sd);
+    StateId n = sd.nstates;
     start_ = other.Start();
     finals_.resize(n);
     offsets_.assign(1, 0);
@@ -353,7 +372,11 @@ class StateIterator {
  public:
   using StateId = typename F::Arc::StateId;
 
-  explicit StateIterator(const F &fst) : n_(fst.NumStates()) {}
+  explicit StateIterator(const F &fst) {
+    StateIteratorData<typename F::Arc> d;
+    fst.InitStateIterator(&d);
+    n_ = d.nstates;
+  }
 
   bool Done() const { return s_ >= n_; }
   StateId Value() const { return s_; }
@@ -361,9 +384,17 @@ class StateIterator {
   void Reset() { s_ = 0; }
 
  private:
-  StateId n_;
+  StateId n_ = 0;
   StateId s_ = 0;
 };
+
+// Number of states of any FST (OpenFst: expanded-fst.h).
+template <class A>
+typename A::StateId CountStates(const Fst<A> &fst) {
+  typename A::StateId n = 0;
+  for (StateIterator<Fst<A>> it(fst); !it.Done(); it.Next()) ++n;
+  return n;
+}
 
 using StdFst = Fst<StdArc>;
 using StdVectorFst = VectorFst<StdArc>;

@@ -20,6 +20,7 @@
 #include "kaldi-decoder_b200/csrc/decodable-itf.h"
 #include "kaldi-decoder_b200/csrc/faster-decoder.h"
 #include "kaldi-decoder_b200/csrc/fst-io.h"
+#include "kaldi-decoder_b200/csrc/lattice-faster-decoder.h"
 #include "kaldi-decoder_b200/csrc/simple-decoder.h"
 #include "kaldifst/csrc/remove-eps-local.h"
 #include "kd_capi.h"
@@ -81,8 +82,8 @@ fst::StdVectorFst FstFromArrays(int32_t num_states, int32_t start,
   return f;
 }
 
-py::tuple FstToArrays(const fst::StdVectorFst &f) {
-  const int32_t n = f.NumStates();
+py::tuple FstToArrays(const fst::Fst<fst::StdArc> &f) {
+  const int32_t n = fst::CountStates(f);
   int64_t e = 0;
   for (int32_t s = 0; s < n; ++s) e += static_cast<int64_t>(f.NumArcs(s));
   py::array_t<int64_t> off(n + 1);
@@ -91,18 +92,26 @@ py::tuple FstToArrays(const fst::StdVectorFst &f) {
   int64_t k = 0;
   off.mutable_data()[0] = 0;
   for (int32_t s = 0; s < n; ++s) {
-    fst::ArcIteratorData<fst::StdArc> d;
-    f.InitArcIterator(s, &d);
-    for (size_t a = 0; a < d.narcs; ++a, ++k) {
-      il.mutable_data()[k] = d.arcs[a].ilabel;
-      ol.mutable_data()[k] = d.arcs[a].olabel;
-      w.mutable_data()[k] = d.arcs[a].weight.Value();
-      ns.mutable_data()[k] = d.arcs[a].nextstate;
+    for (fst::ArcIterator<fst::Fst<fst::StdArc>> aiter(f, s); !aiter.Done(); aiter.Next(), ++k) {
+      const fst::StdArc &arc = aiter.Value();
+      il.mutable_data()[k] = arc.ilabel;
+      ol.mutable_data()[k] = arc.olabel;
+      w.mutable_data()[k] = arc.weight.Value();
+      ns.mutable_data()[k] = arc.nextstate;
     }
     off.mutable_data()[s + 1] = k;
     fin.mutable_data()[s] = f.Final(s).Value();
   }
   return py::make_tuple(n, f.Start(), off, il, ol, w, ns, fin);
+}
+
+std::vector<std::tuple<int, int, float, int>> StdArcsOf(const fst::Fst<fst::StdArc> &f, int s) {
+  std::vector<std::tuple<int, int, float, int>> out;
+  for (fst::ArcIterator<fst::Fst<fst::StdArc>> aiter(f, s); !aiter.Done(); aiter.Next()) {
+    const fst::StdArc &arc = aiter.Value();
+    out.emplace_back(arc.ilabel, arc.olabel, arc.weight.Value(), arc.nextstate);
+  }
+  return out;
 }
 
 }  // namespace
@@ -111,33 +120,52 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
   m.doc() = "B200-native kaldi-decoder: pybind11 binding";
 
   // ---- FST value types (stand-ins for kaldifst.StdVectorFst / kaldifst.Lattice)
-  py::class_<fst::StdVectorFst>(m, "StdVectorFst")
+  // The reference's constructors take kaldifst's Fst<StdArc> / VectorFst / ConstFst
+  // (python/csrc/faster-decoder.cc:34-42): the same three types here.
+  py::class_<fst::StdFst>(m, "StdFst")
+      .def_property_readonly("start", &fst::StdFst::Start)
+      .def_property_readonly("num_states",
+                             [](const fst::StdFst &f) { return fst::CountStates(f); })
+      .def("num_arcs", &fst::StdFst::NumArcs, py::arg("state"))
+      .def("final", [](const fst::StdFst &f, int s) { return f.Final(s).Value(); },
+           py::arg("state"))
+      .def("arcs", &StdArcsOf, py::arg("state"),
+           "(ilabel, olabel, weight, nextstate) of every arc leaving `state`")
+      .def("to_arrays", &FstToArrays)
+      .def("to_str", [](const fst::StdFst &f) { return WriteFstText(f); })
+      .def("write", [](const fst::StdFst &f, const std::string &p) { WriteFst(f, p); },
+           py::arg("filename"), "OpenFst binary, fst type \"vector\"")
+      .def_property_readonly("fst_type", [](const fst::StdFst &f) { return f.Type(); });
+
+  py::class_<fst::StdVectorFst, fst::StdFst>(m, "StdVectorFst")
       .def(py::init<>())
+      .def(py::init([](const fst::StdFst &f) { return fst::StdVectorFst(f); }), py::arg("fst"))
       .def_static("from_arrays", &FstFromArrays, py::arg("num_states"), py::arg("start"),
                   py::arg("row_offsets"), py::arg("ilabel"), py::arg("olabel"), py::arg("weight"),
                   py::arg("nextstate"), py::arg("final"))
       .def_static("read", &ReadFst, py::arg("filename"))
-      .def_static("from_str", &ReadFstText, py::arg("s"), py::arg("acceptor") = false)
-      .def("write", [](const fst::StdVectorFst &f, const std::string &p) { WriteFst(f, p); },
-           py::arg("filename"))
-      .def("to_str", [](const fst::StdVectorFst &f) { return WriteFstText(f); })
-      .def("to_arrays", &FstToArrays)
-      .def_property_readonly("start", &fst::StdVectorFst::Start)
-      .def_property_readonly("num_states", &fst::StdVectorFst::NumStates)
-      .def("num_arcs", &fst::StdVectorFst::NumArcs, py::arg("state"))
-      .def("final", [](const fst::StdVectorFst &f, int s) { return f.Final(s).Value(); },
-           py::arg("state"))
-      .def("arcs",
-           [](const fst::StdVectorFst &f, int s) {
-             std::vector<std::tuple<int, int, float, int>> out;
-             fst::ArcIteratorData<fst::StdArc> d;
-             f.InitArcIterator(s, &d);
-             for (size_t a = 0; a < d.narcs; ++a)
-               out.emplace_back(d.arcs[a].ilabel, d.arcs[a].olabel, d.arcs[a].weight.Value(),
-                                d.arcs[a].nextstate);
-             return out;
-           },
-           py::arg("state"), "(ilabel, olabel, weight, nextstate) of every arc leaving `state`");
+      .def_static("from_str", &ReadFstText, py::arg("s"), py::arg("acceptor") = false);
+
+  // Immutable CSR form: what an OpenFst "const" file holds and what the device graph is
+  // built from without an intermediate copy per state.
+  py::class_<fst::StdConstFst, fst::StdFst>(m, "StdConstFst")
+      .def(py::init<>())
+      .def(py::init([](const fst::StdFst &f) { return fst::StdConstFst(f); }), py::arg("fst"))
+      .def_static("read", [](const std::string &p) { return fst::StdConstFst(ReadFst(p)); },
+                  py::arg("filename"))
+      .def_static(
+          "from_arrays",
+          [](int32_t num_states, int32_t start,
+             const py::array_t<int64_t, py::array::c_style | py::array::forcecast> &row_off,
+             const py::array_t<int32_t, py::array::c_style | py::array::forcecast> &il,
+             const py::array_t<int32_t, py::array::c_style | py::array::forcecast> &ol,
+             const FloatArray &w,
+             const py::array_t<int32_t, py::array::c_style | py::array::forcecast> &ns,
+             const FloatArray &fin) {
+            return fst::StdConstFst(FstFromArrays(num_states, start, row_off, il, ol, w, ns, fin));
+          },
+          py::arg("num_states"), py::arg("start"), py::arg("row_offsets"), py::arg("ilabel"),
+          py::arg("olabel"), py::arg("weight"), py::arg("nextstate"), py::arg("final"));
 
   py::class_<fst::Lattice>(m, "Lattice")
       .def(py::init<>())
@@ -152,11 +180,11 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def("arcs",
            [](const fst::Lattice &f, int s) {
              std::vector<std::tuple<int, int, float, float, int>> out;
-             fst::ArcIteratorData<fst::LatticeArc> d;
-             f.InitArcIterator(s, &d);
-             for (size_t a = 0; a < d.narcs; ++a)
-               out.emplace_back(d.arcs[a].ilabel, d.arcs[a].olabel, d.arcs[a].weight.Value1(),
-                                d.arcs[a].weight.Value2(), d.arcs[a].nextstate);
+             for (fst::ArcIterator<fst::Lattice> aiter(f, s); !aiter.Done(); aiter.Next()) {
+               const fst::LatticeArc &arc = aiter.Value();
+               out.emplace_back(arc.ilabel, arc.olabel, arc.weight.Value1(), arc.weight.Value2(),
+                                arc.nextstate);
+             }
              return out;
            },
            py::arg("state"), "(ilabel, olabel, graph, acoustic, nextstate) of every arc");
@@ -195,6 +223,32 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def_readwrite("hash_ratio", &FasterDecoderOptions::hash_ratio)
       .def("__str__", &FasterDecoderOptions::ToString);
 
+  // lattice-faster-decoder.h:23-134 of the reference (the struct only; see that header)
+  py::class_<LatticeFasterDecoderConfig>(m, "LatticeFasterDecoderConfig")
+      .def(py::init<float, int32_t, int32_t, float, int32_t, bool, float, float, float, int32_t,
+                    int32_t>(),
+           py::arg("beam") = 16.0, py::arg("max_active") = std::numeric_limits<int32_t>::max(),
+           py::arg("min_active") = 200, py::arg("lattice_beam") = 10.0,
+           py::arg("prune_interval") = 25, py::arg("determinize_lattice") = true,
+           py::arg("beam_delta") = 0.5, py::arg("hash_ratio") = 2.0, py::arg("prune_scale") = 0.1,
+           py::arg("memory_pool_tokens_block_size") = 1 << 8,
+           py::arg("memory_pool_links_block_size") = 1 << 8)
+      .def_readwrite("beam", &LatticeFasterDecoderConfig::beam)
+      .def_readwrite("max_active", &LatticeFasterDecoderConfig::max_active)
+      .def_readwrite("min_active", &LatticeFasterDecoderConfig::min_active)
+      .def_readwrite("lattice_beam", &LatticeFasterDecoderConfig::lattice_beam)
+      .def_readwrite("prune_interval", &LatticeFasterDecoderConfig::prune_interval)
+      .def_readwrite("determinize_lattice", &LatticeFasterDecoderConfig::determinize_lattice)
+      .def_readwrite("beam_delta", &LatticeFasterDecoderConfig::beam_delta)
+      .def_readwrite("hash_ratio", &LatticeFasterDecoderConfig::hash_ratio)
+      .def_readwrite("prune_scale", &LatticeFasterDecoderConfig::prune_scale)
+      .def_readwrite("memory_pool_tokens_block_size",
+                     &LatticeFasterDecoderConfig::memory_pool_tokens_block_size)
+      .def_readwrite("memory_pool_links_block_size",
+                     &LatticeFasterDecoderConfig::memory_pool_links_block_size)
+      .def("check", &LatticeFasterDecoderConfig::Check)
+      .def("__str__", &LatticeFasterDecoderConfig::ToString);
+
   py::class_<DeviceConfig>(m, "DeviceConfig")
       .def(py::init<>())
       .def_readwrite("device", &DeviceConfig::device)
@@ -204,13 +258,22 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def_readwrite("chunk_frames", &DeviceConfig::chunk_frames);
 
   py::class_<DeviceGraph, std::shared_ptr<DeviceGraph>>(m, "DeviceGraph")
-      .def(py::init([](const fst::StdVectorFst &f, int32_t device) {
+      .def(py::init([](const fst::StdFst &f, int32_t device) {
              return std::make_shared<DeviceGraph>(f, device);
            }),
            py::arg("fst"), py::arg("device") = 0);
 
   py::class_<FasterDecoder>(m, "FasterDecoder")
+      // the reference's three overloads (python/csrc/faster-decoder.cc:34-42)
+      .def(py::init([](const fst::StdFst &f, const FasterDecoderOptions &config) {
+             return std::make_unique<FasterDecoder>(f, config);
+           }),
+           py::arg("fst"), py::arg("config"))
       .def(py::init([](const fst::StdVectorFst &f, const FasterDecoderOptions &config) {
+             return std::make_unique<FasterDecoder>(f, config);
+           }),
+           py::arg("fst"), py::arg("config"))
+      .def(py::init([](const fst::StdConstFst &f, const FasterDecoderOptions &config) {
              return std::make_unique<FasterDecoder>(f, config);
            }),
            py::arg("fst"), py::arg("config"))
@@ -237,7 +300,7 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
 
   // ---- SimpleDecoder (kaldi-decoder/python/csrc/simple-decoder.cc:14-44)
   py::class_<SimpleDecoder>(m, "SimpleDecoder")
-      .def(py::init([](const fst::StdVectorFst &f, float beam) {
+      .def(py::init([](const fst::StdFst &f, float beam) {
              return std::make_unique<SimpleDecoder>(f, beam);
            }),
            py::arg("fst"), py::arg("beam"))
@@ -263,7 +326,7 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
 
   // ---- additive: many lanes per call
   py::class_<BatchFasterDecoder>(m, "BatchFasterDecoder")
-      .def(py::init([](const fst::StdVectorFst &f, const FasterDecoderOptions &config,
+      .def(py::init([](const fst::StdFst &f, const FasterDecoderOptions &config,
                        int32_t max_lanes, const DeviceConfig &dev) {
              return std::make_unique<BatchFasterDecoder>(f, config, max_lanes, dev);
            }),
@@ -308,6 +371,41 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
           py::arg("offsets") = std::vector<int32_t>(), py::arg("max_num_frames") = -1,
           py::arg("device_memory") = false,
           "Raw float32 row-major matrices by address (e.g. torch tensor.data_ptr(), host or CUDA)")
+      .def(
+          "decode_async",
+          [](BatchFasterDecoder &self, const std::vector<int32_t> &lanes,
+             const std::vector<uintptr_t> &ptrs, const std::vector<int32_t> &rows, int32_t cols,
+             bool device_memory, uintptr_t producer_stream) {
+            std::vector<const float *> mats;
+            for (auto p : ptrs) mats.push_back(reinterpret_cast<const float *>(p));
+            py::gil_scoped_release nogil;
+            return self.DecodeAsync(lanes, mats, rows, cols, device_memory,
+                                    reinterpret_cast<void *>(producer_stream));
+          },
+          py::arg("lanes"), py::arg("ptrs"), py::arg("rows"), py::arg("cols"),
+          py::arg("device_memory") = false, py::arg("producer_stream") = 0,
+          "Deferred InitDecoding + AdvanceDecoding over all rows + GetBestPath of the lanes, one "
+          "kernel launch; returns a ticket at once.  The matrices (raw float32 row-major, by "
+          "address) must stay valid until wait()/get_results().  producer_stream: the CUDA "
+          "stream device matrices were produced on (e.g. torch.cuda.current_stream().cuda_stream)")
+      .def(
+          "wait",
+          [](BatchFasterDecoder &self, int64_t ticket) {
+            py::gil_scoped_release nogil;
+            self.Wait(ticket);
+          },
+          py::arg("ticket") = -1)
+      .def(
+          "get_results",
+          [](BatchFasterDecoder &self, int64_t ticket, bool use_final_probs) {
+            std::vector<int32_t> lanes;
+            std::vector<fst::Lattice> lats;
+            std::vector<bool> ok;
+            self.GetResults(ticket, &lanes, &lats, &ok, use_final_probs);
+            return py::make_tuple(lanes, ok, lats);
+          },
+          py::arg("ticket"), py::arg("use_final_probs") = true,
+          "(lanes, ok, lattices) of a decode_async call, without launching anything")
       .def("num_frames_decoded", &BatchFasterDecoder::NumFramesDecoded, py::arg("lane"))
       .def("reached_final", &BatchFasterDecoder::ReachedFinal, py::arg("lane"))
       .def(

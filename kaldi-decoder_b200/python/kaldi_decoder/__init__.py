@@ -9,9 +9,11 @@ __init__.py:1-9) keep their import path, signatures and defaults:
 `LatticeSimpleDecoder` and `LatticeSimpleDecoderConfig` are not part of the
 accelerated path and are not provided.
 
-Additions: `StdVectorFst`, `Lattice`, `get_linear_symbol_sequence` (stand-ins for
+Additions: `StdFst`, `StdVectorFst`, `StdConstFst`, `Lattice`, `get_linear_symbol_sequence` (stand-ins for
 the kaldifst types the reference's bindings exchange -- kaldifst is a separate
-package), `BatchFasterDecoder`, `DeviceGraph`, `DeviceConfig`.
+package), `LatticeFasterDecoderConfig` (the options struct only), `BatchFasterDecoder` (many
+lanes per call; `decode_async` / `wait` / `get_results` for deferred, overlapped batches),
+`DeviceGraph`, `DeviceConfig`.
 
 The extension module needs the CUDA library built for sm_100a and a GPU at run
 time; there is no CPU fallback.
@@ -26,7 +28,10 @@ try:
         FasterDecoder,
         FasterDecoderOptions,
         Lattice,
+        LatticeFasterDecoderConfig,
         SimpleDecoder,
+        StdConstFst,
+        StdFst,
         StdVectorFst,
         device_count,
         get_linear_symbol_sequence,
@@ -37,7 +42,7 @@ except ImportError as e:  # pragma: no cover
         "to load (build it with `python kaldi-decoder_b200/build.py`; it links "
         "kaldi-decoder_b200/lib/libkd_b200.so, sm_100a, no CPU fallback): " + str(e)) from e
 
-__version__ = "0.3.0+b200.r1"
+__version__ = "0.3.0+b200.r2"
 
 
 def fst_from_kaldifst(fst) -> "StdVectorFst":
@@ -76,31 +81,71 @@ def _iter_kaldifst(kaldifst, fst, s):
         it.next()
 
 
-def advance_decoding_cuda(decoder: "BatchFasterDecoder", lanes, tensors, offsets=None,
-                          max_num_frames: int = -1) -> None:
-    """`BatchFasterDecoder.advance_decoding` for log-probs that already live on the GPU.
-
-    `tensors[i]` is a contiguous float32 `[T_i, V]` CUDA array for lane `lanes[i]`: a torch
-    tensor, or anything exposing `__cuda_array_interface__` (CuPy, Numba).  No copy is made and
-    the call returns when the frames are decoded, so the arrays only have to outlive the call.
-    """
-    ptrs, rows, cols = [], [], None
+def _cuda_matrices(tensors):
+    """(ptrs, rows, cols, producer stream handle) of contiguous float32 [T, V] CUDA arrays."""
+    ptrs, rows, cols, stream, device = [], [], None, 0, None
     for t in tensors:
         if hasattr(t, "data_ptr"):  # torch
             if not t.is_cuda or str(t.dtype) != "torch.float32" or not t.is_contiguous() or t.dim() != 2:
                 raise ValueError("expected contiguous float32 [T, V] CUDA tensors")
             ptr, shape = int(t.data_ptr()), tuple(t.shape)
+            dev = int(t.device.index or 0)
+            if not stream:
+                import torch
+                # the stream the tensors were (or are being) produced on: the search is ordered
+                # behind it -- the decoder's own streams do not synchronise with torch's
+                stream = int(torch.cuda.current_stream(t.device).cuda_stream)
         else:
             cai = t.__cuda_array_interface__
             if cai["typestr"] not in ("<f4", "=f4") or len(cai["shape"]) != 2 or cai.get("strides"):
                 raise ValueError("expected contiguous float32 [T, V] CUDA arrays")
             ptr, shape = int(cai["data"][0]), tuple(cai["shape"])
+            dev = None
+            if cai.get("stream") not in (None, 0, 1, 2) and not stream:
+                stream = int(cai["stream"])
+        if dev is not None:
+            if device is None:
+                device = dev
+            elif device != dev:
+                raise ValueError("all matrices must live on the same CUDA device")
         if cols is None:
             cols = int(shape[1])
         elif cols != int(shape[1]):
             raise ValueError("all matrices must have the same number of columns")
         ptrs.append(ptr)
         rows.append(int(shape[0]))
-    decoder.advance_decoding_ptrs(list(lanes), ptrs, rows, int(cols or 0),
+    return ptrs, rows, int(cols or 0), stream, device
+
+
+def advance_decoding_cuda(decoder: "BatchFasterDecoder", lanes, tensors, offsets=None,
+                          max_num_frames: int = -1, device: int = None) -> None:
+    """`BatchFasterDecoder.advance_decoding` for log-probs that already live on the GPU.
+
+    `tensors[i]` is a contiguous float32 `[T_i, V]` CUDA array for lane `lanes[i]`: a torch
+    tensor, or anything exposing `__cuda_array_interface__` (CuPy, Numba).  No copy is made and
+    the call returns when the frames are decoded, so the arrays only have to outlive the call.
+
+    Stream ordering: the decoder launches on its own non-blocking streams.  For torch tensors
+    the current stream of their device is synchronised first, so work enqueued on it (the
+    log_softmax that produced the tensors) is complete before the search reads them; arrays
+    produced on other streams must be synchronised by the caller.  `device` (the decoder's
+    device index), when given, is checked against the tensors' device.
+    """
+    ptrs, rows, cols, stream, dev = _cuda_matrices(tensors)
+    if device is not None and dev is not None and int(device) != dev:
+        raise ValueError(f"tensors live on cuda:{dev}, the decoder on cuda:{device}")
+    if stream:
+        import torch
+        torch.cuda.current_stream(dev).synchronize()
+    decoder.advance_decoding_ptrs(list(lanes), ptrs, rows, cols,
                                   list(offsets) if offsets is not None else [],
                                   int(max_num_frames), True)
+
+
+def decode_cuda_async(decoder: "BatchFasterDecoder", lanes, tensors) -> int:
+    """Deferred `decode` of CUDA log-prob matrices (see `advance_decoding_cuda` for the accepted
+    arrays): InitDecoding + all frames + best-path selection in one kernel launch, ordered
+    behind the stream the tensors were produced on (no host synchronisation).  Returns a ticket
+    for `decoder.wait(ticket)` / `decoder.get_results(ticket)`; keep the tensors alive until then."""
+    ptrs, rows, cols, stream, _ = _cuda_matrices(tensors)
+    return decoder.decode_async(list(lanes), ptrs, rows, cols, True, stream)

@@ -359,3 +359,52 @@ def test_cuda_tensors_are_decoded_in_place():
         assert seqs[u][3] == seqs[u + 2][3]
     with pytest.raises(ValueError):
         kd.advance_decoding_cuda(bd, [0], [torch.zeros(3, 4)])
+
+
+def test_const_fst_overload_and_deferred_batches_through_the_python_package():
+    """The reference's ConstFst / Fst constructor overloads (python/csrc/faster-decoder.cc:
+    34-42) and the additive deferred API of BatchFasterDecoder, against the golden fixture."""
+    import kaldi_decoder as kd
+    gc = GoldenCase("hlg300_peaky")
+    g = gc.graph
+    o = gc.opts
+    vfst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                       g.weight, g.nextstate, g.final)
+    cfst = kd.StdConstFst(vfst)
+    opts = kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"], min_active=o["min_active"])
+    for f in (cfst, vfst):
+        dec = kd.FasterDecoder(f, opts)
+        dec.decode(kd.DecodableCtc(gc.logp(0)))
+        ok, best = dec.get_best_path()
+        assert ok and dec.reached_final() == gc.reached_final(0)
+        assert kd.get_linear_symbol_sequence(best)[2] == [int(x) for x in gc.best(0).osyms]
+    # deferred batches: two calls in flight on disjoint lanes
+    n = min(4, gc.n_utts)
+    bd = kd.BatchFasterDecoder(cfst, opts, max_lanes=2 * n)
+    mats = [np.ascontiguousarray(gc.logp(u), dtype=np.float32) for u in range(n)]
+    ptrs = [m.ctypes.data for m in mats]
+    rows = [m.shape[0] for m in mats]
+    cols = mats[0].shape[1]
+    t0 = bd.decode_async(list(range(n)), ptrs, rows, cols)
+    t1 = bd.decode_async(list(range(n, 2 * n)), ptrs, rows, cols)
+    for t, base in ((t0, 0), (t1, n)):
+        lanes, oks, lats = bd.get_results(t)
+        assert lanes == list(range(base, base + n))
+        for u in range(n):
+            assert oks[u]
+            ok2, isyms, osyms, (gcost, acost) = kd.get_linear_symbol_sequence(lats[u])
+            want = gc.best(u, True)
+            assert ok2 and isyms == [int(x) for x in want.isyms] and osyms == [int(x) for x in want.osyms]
+            assert rel_close(gcost + acost, want.total_cost, 1e-4)
+            assert bd.reached_final(base + u) == gc.reached_final(u)
+    bd.wait()
+    # CUDA tensors, ordered behind the stream that produces them
+    torch = pytest.importorskip("torch")
+    dev = [torch.from_numpy(m).cuda() for m in mats]
+    t = kd.decode_cuda_async(bd, list(range(n)), dev)
+    lanes, oks, lats = bd.get_results(t)
+    for u in range(n):
+        assert kd.get_linear_symbol_sequence(lats[u])[2] == [int(x) for x in gc.best(u).osyms]
+    kd.advance_decoding_cuda(bd, [0], [dev[0][:0]], device=0)  # nothing to decode: a no-op
+    with pytest.raises(ValueError):
+        kd.advance_decoding_cuda(bd, [0], [dev[0]], device=1)

@@ -165,3 +165,170 @@ def test_shard_helpers():
     assert sorted(sum(parts, [])) == list(range(7))
     loads = [sum([10, 1, 1, 1, 9, 2, 8][i] for i in p) for p in parts]
     assert max(loads) - min(loads) <= 2
+
+
+# ---------------------------------------------------------------- SURVEY section 8, rows f1 / f4
+
+def test_lattice_faster_decoder_config_matches_the_reference_struct():
+    """lattice-faster-decoder.h:23-134: defaults, field names, ToString, Check."""
+    import kaldi_decoder as kd
+    c = kd.LatticeFasterDecoderConfig()
+    assert (c.beam, c.max_active, c.min_active, c.lattice_beam, c.prune_interval,
+            c.determinize_lattice, c.beam_delta, c.hash_ratio, c.memory_pool_tokens_block_size,
+            c.memory_pool_links_block_size) == (16.0, 2**31 - 1, 200, 10.0, 25, True, 0.5, 2.0, 256, 256)
+    assert abs(c.prune_scale - 0.1) < 1e-7
+    assert str(kd.LatticeFasterDecoderConfig(beam=12, max_active=5000, determinize_lattice=False)) == (
+        "LatticeFasterDecoderConfig(beam=12, max_active=5000, min_active=200, lattice_beam=10, "
+        "prune_interval=25, determinize_lattice=False, beam_delta=0.5, hash_ratio=2, "
+        "prune_scale=0.1, memory_pool_tokens_block_size=256, memory_pool_links_block_size=256)")
+    c.lattice_beam = 6.5
+    assert c.lattice_beam == 6.5
+    c.check()
+    c.prune_scale = 1.5
+    with pytest.raises(RuntimeError):
+        c.check()
+
+
+def _fst_header(fst_type, version, flags, start, num_states, num_arcs):
+    import struct
+    def s(x):
+        return struct.pack("<i", len(x)) + x.encode()
+    return (struct.pack("<i", 2125659606) + s(fst_type) + s("standard")
+            + struct.pack("<iiQqqq", version, flags, 0, start, num_states, num_arcs))
+
+
+def _symbol_table(name, symbols):
+    import struct
+    b = struct.pack("<i", 2125658996) + struct.pack("<i", len(name)) + name.encode()
+    b += struct.pack("<qq", len(symbols), len(symbols))
+    for k, sym in enumerate(symbols):
+        b += struct.pack("<i", len(sym)) + sym.encode() + struct.pack("<q", k)
+    return b
+
+
+# state -> (final weight, [(ilabel, olabel, weight, nextstate)])
+_TOY = {0: (float("inf"), [(1, 5, 0.5, 1), (0, 7, 0.25, 2), (3, 0, 1.5, 0)]),
+        1: (float("inf"), [(2, 0, 0.0, 2)]),
+        2: (0.75, [])}
+
+
+def _vector_body():
+    import struct
+    b = b""
+    for s in sorted(_TOY):
+        fin, arcs = _TOY[s]
+        b += struct.pack("<fq", fin, len(arcs))
+        for il, ol, w, ns in arcs:
+            b += struct.pack("<iifi", il, ol, w, ns)
+    return b
+
+
+def _const_body(prefix_len, aligned):
+    import struct
+    def pad(n):
+        return b"\0" * ((16 - n % 16) % 16) if aligned else b""
+    b = pad(prefix_len)
+    pos = 0
+    for s in sorted(_TOY):
+        fin, arcs = _TOY[s]
+        nie = sum(1 for a in arcs if a[0] == 0)
+        noe = sum(1 for a in arcs if a[1] == 0)
+        b += struct.pack("<fIIII", fin, pos, len(arcs), nie, noe)
+        pos += len(arcs)
+    b += pad(prefix_len + len(b))
+    for s in sorted(_TOY):
+        for il, ol, w, ns in _TOY[s][1]:
+            b += struct.pack("<iifi", il, ol, w, ns)
+    return b
+
+
+@pytest.mark.parametrize("kind", ["vector", "vector+symbols", "const-v2", "const-v1-aligned",
+                                  "const-flag-aligned", "const+symbols-aligned"])
+def test_openfst_binary_reader_on_byte_level_fixtures(kind, tmp_path):
+    """Files assembled byte by byte from OpenFst's published layout (SURVEY.md App. B.5;
+    fst.cc FstHeader::Read, vector-fst.h / const-fst.h Read, symbol-table.cc): header, optional
+    embedded symbol tables (skipped), `vector` body, `const` body with and without 16-byte
+    alignment.  (No real OpenFst is available to write them; the layout is from its source.)"""
+    import kaldi_decoder as kd
+    n_arcs = sum(len(a) for _, a in _TOY.values())
+    syms = b""
+    flags = 0
+    if "symbols" in kind:
+        syms = _symbol_table("isyms", ["<eps>", "a", "b", "c"]) + _symbol_table("osyms", ["<eps>", "x"])
+        flags |= 3
+    if kind.startswith("vector"):
+        data = _fst_header("vector", 2, flags, 0, len(_TOY), n_arcs) + syms + _vector_body()
+    else:
+        version = 1 if "v1" in kind else 2
+        if "flag-aligned" in kind or "symbols-aligned" in kind:
+            flags |= 4
+        aligned = version == 1 or (flags & 4) != 0
+        head = _fst_header("const", version, flags, 0, len(_TOY), n_arcs) + syms
+        data = head + _const_body(len(head), aligned)
+    path = tmp_path / (kind + ".fst")
+    path.write_bytes(data)
+    for cls in (kd.StdVectorFst, kd.StdConstFst):
+        f = cls.read(str(path))
+        assert isinstance(f, kd.StdFst)
+        assert f.fst_type == ("vector" if cls is kd.StdVectorFst else "const")
+        assert f.start == 0 and f.num_states == len(_TOY)
+        for s, (fin, arcs) in _TOY.items():
+            assert f.final(s) == np.float32(fin)
+            assert f.arcs(s) == [(il, ol, float(np.float32(w)), ns) for il, ol, w, ns in arcs]
+    # truncated files fail loudly
+    (tmp_path / "cut.fst").write_bytes(data[:len(data) - 5])
+    with pytest.raises(RuntimeError):
+        kd.StdVectorFst.read(str(tmp_path / "cut.fst"))
+
+
+def test_const_and_vector_fst_types_and_constructor_overloads():
+    """python/csrc/faster-decoder.cc:34-42: FasterDecoder(fst, config) is overloaded on
+    Fst / VectorFst / ConstFst.  Without a GPU the constructors must get as far as the
+    device ("no CPU fallback"), not fail on the argument type."""
+    import kaldi_decoder as kd
+    g = small_graph("HL")
+    v = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel, g.weight,
+                                    g.nextstate, g.final)
+    c = kd.StdConstFst(v)
+    c2 = kd.StdConstFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel, g.weight,
+                                    g.nextstate, g.final)
+    assert c.num_states == v.num_states == c2.num_states == g.num_states
+    for a, b in zip(v.to_arrays(), c.to_arrays()):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    assert kd.StdVectorFst(c).to_str() == v.to_str() == c2.to_str()
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present (covered by the GPU tests)")
+    opts = kd.FasterDecoderOptions(beam=8.0)
+    for f in (v, c):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            kd.FasterDecoder(f, opts)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            kd.SimpleDecoder(f, 8.0)
+    with pytest.raises(TypeError):
+        kd.FasterDecoder("not an fst", opts)
+
+
+def test_host_sources_compile_against_an_openfst_shaped_fst_h(tmp_path):
+    """with OpenFst on the include path, csrc/minifst/fst is dropped.  The
+    host sources are syntax-checked against tests/openfst_shape (OpenFst's Fst / ExpandedFst /
+    MutableFst split: no NumStates() on Fst<Arc>, iterator data with a polymorphic base);
+    a translation unit that does call Fst::NumStates() must be rejected by the same header."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    inc = ["-I", os.path.join(ROOT, "tests", "openfst_shape"),
+           "-I", os.path.join(ROOT, "kaldi-decoder_b200", "csrc", "minifst"),
+           "-I", os.path.join(ROOT, "include"), "-I", ROOT]
+    for src in ("faster-decoder.cc", "simple-decoder.cc", "fst-io.cc", "decodable-ctc.cc"):
+        r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", *inc,
+                            os.path.join(ROOT, "kaldi-decoder_b200", "csrc", src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, src + "\n" + r.stderr[-3000:]
+    bad = tmp_path / "bad.cc"
+    bad.write_text('#include "fst/fst.h"\n'
+                   "int f(const fst::Fst<fst::StdArc> &g) { return g.NumStates(); }\n")
+    r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", *inc, str(bad)], capture_output=True,
+                       text=True)
+    assert r.returncode != 0 and "NumStates" in r.stderr
