@@ -64,15 +64,21 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--check", action="store_true", help="compare a sample with the reference")
-    ap.add_argument("--groups", type=int, default=2,
-                    help="lane groups taking turns (2: steps are enqueued one ahead; 1: sequential)")
+    ap.add_argument("--groups", type=int, default=0,
+                    help="lane groups taking turns (default per config; 1: sequential steps)")
     return ap.parse_args()
 
 
 CONFIG_LANES = {"C1": 64, "C2": 256, "C3": 1024, "C4": 1024}
+# Lane groups taking turns (steps in flight) and threads per lane.  A step of C1 / C2 is 64 /
+# 256 utterances: one such batch cannot fill 148 SMs, so more steps are kept in flight (the
+# lanes of later steps start as soon as a CTA slot is free) and lanes run at the width that is
+# best when the chip is full (160 threads, 7 lanes per SM).
+CONFIG_GROUPS = {"C1": 16, "C2": 8, "C3": 2, "C4": 2}
+CONFIG_THREADS = {"C1": 160, "C2": 160, "C3": 0, "C4": 0}
 # tokens alive in one frame must stay below half of this (measured maxima: C1 500, C2 146k,
 # C3 49k, C4 142k tokens)
-CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 20, "C3": 1 << 18, "C4": 1 << 19}
+CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 19, "C3": 1 << 18, "C4": 1 << 19}
 CONFIG_NAME = {
     "C1": "H-500 CTC topology, 64 utts x T=1000 x V=500, beam 20, max_active 7000",
     "C2": "HL 200k-word lexicon trie, 256 utts x T=1000 x V=500, beam 20, max_active 7000",
@@ -275,11 +281,11 @@ def main():
     # are enqueued one ahead (kd_decoder_advance_async), so the lanes of step k+1 take over
     # the SMs as the slowest lanes of step k finish, and (end to end) the upload of step k+1
     # runs under the search of step k.  --groups 1 gives strictly sequential steps.
-    n_groups = max(1, args.groups)
+    n_groups = args.groups if args.groups > 0 else CONFIG_GROUPS[args.config]
     dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes * n_groups,
                            hash_capacity=args.hash_capacity or CONFIG_HASH[args.config],
                            arena_records=args.arena_records,
-                           threads_per_lane=args.threads_per_lane,
+                           threads_per_lane=args.threads_per_lane or CONFIG_THREADS[args.config],
                            chunk_frames=args.chunk_frames)
     # every rank decodes its own utterances (seed differs per rank): weak scaling
     logp = make_device_logprobs(g, lanes, T, args.seed + 7919 * rank, args.peak, dev)

@@ -405,6 +405,6 @@ def test_const_fst_overload_and_deferred_batches_through_the_python_package():
     lanes, oks, lats = bd.get_results(t)
     for u in range(n):
         assert kd.get_linear_symbol_sequence(lats[u])[2] == [int(x) for x in gc.best(u).osyms]
-    kd.advance_decoding_cuda(bd, [0], [dev[0][:0]], device=0)  # nothing to decode: a no-op
+    kd.advance_decoding_cuda(bd, [0], [dev[0][:0]], offsets=[rows[0]], device=0)  # nothing new: a no-op
     with pytest.raises(ValueError):
         kd.advance_decoding_cuda(bd, [0], [dev[0]], device=1)
