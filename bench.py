@@ -1,22 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- decoded frames/s of the token-passing search on synthetic HLG.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config C1..C4]
 
-One "step" = one pass of the hot path over one batch of synthetic input:
-InitDecoding + AdvanceDecoding over all frames + GetBestPath for every
-utterance lane of the workload (BASELINE.json configs[2]: HLG with a synthetic
-3-gram LM, ~5M arcs, 1024 utterances x T=1000 x V=500, beam 20, max_active
-7000; one graph replica and 1024 lanes per GPU -> weak scaling).
+One "step" = one pass of the hot path over one batch of synthetic input: InitDecoding +
+AdvanceDecoding over all frames + GetBestPath for every utterance lane of the workload
+(default: BASELINE.json configs[2], HLG with a synthetic 3-gram LM, ~5M arcs, 1024 utterances
+x T=1000 x V=500, beam 20, max_active 7000; one graph replica and 1024 utterances per step
+per GPU -> weak scaling).  A step is ONE kernel launch (kd_decoder_advance_async with
+KD_ADVANCE_INIT | KD_ADVANCE_FINALIZE) plus the copies around it.  Steps are enqueued one
+ahead on alternating lane groups: the lanes of step k+1 take over the SMs as the slowest
+lanes of step k finish, and the upload of step k+1 runs under the search of step k.  Every
+step's work lies inside the timed region; `--groups 1` gives strictly sequential steps.
 
-  value  : whole-job frames/s with the log-probs already resident in HBM.
-  e2e    : the same through the C ABI with HOST (pinned) log-prob buffers:
-           host->device copies and the device->host read of the best paths are
-           inside the timed region.
-  roofline: algorithmic bytes (counted by the kernel) / the
-           search kernel's CUDA-event duration, against MEASURED_PEAKS.json.
-  cpu_baseline: the reference's own faster-decoder.cc (oracle/_ref), one
-           utterance per host thread, on a bounded sample of the same workload.
+  value  : whole-job frames/s with the log-probs already resident in HBM (K steps, wall time
+           between two barriers, max over ranks).
+  e2e    : the same through the C ABI with HOST (pinned) log-prob buffers: the host->device
+           copies and the device->host read of the best paths are inside the timed region.
+  roofline: .achieved = algorithmic bytes (counted by the kernel: the
+           out-degree of every expanded token, whether or not a label table let the kernel
+           skip the arc) / device time per launch (CUDA events on the launching streams,
+           first launch's start to last launch's end over the launches, timed region);
+           .touched_* = bytes the kernel actually requests, from its own counters;
+           .traffic = DRAM bytes of this build measured with ncu (profiles/r2_dram_bytes.json).
+  cpu_baseline: the reference's own faster-decoder.cc (oracle/_ref), one utterance per host
+           thread, on a bounded sample of the same batch; parity_sample classifies that
+           sample by SURVEY 8(d)'s protocol (identical / exact tie / real, never-binding /
+           binding utterances).
 
 `--impl reference` times that CPU reference alone (rank 0 only).
 Prints ONE JSON line on rank 0.
@@ -109,6 +119,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if os.environ.get("KD_BENCH_NO_SAMPLER"):  # (diagnosis: is nvidia-smi perturbing the run?)
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",

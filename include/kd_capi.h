@@ -191,7 +191,7 @@ KD_API int kd_decoder_wait(kd_decoder *d, int64_t ticket);
  * *lanes lists the *num_lanes lanes the call advanced, in call order; lane i's arcs are
  * four arrays of num_arcs[i] words -- ilabel, olabel (int32), graph cost, acoustic cost
  * (float) -- starting at (*words)[(*word_offsets)[4 * i + 0..3]].  The pointers address
- * pinned host memory of the decoder and stay valid until the 16th-next
+ * pinned host memory of the decoder and stay valid until the third-next
  * kd_decoder_advance_async call or the decoder's destruction.  ok / reached_final /
  * final_weight2 (2 per lane) as kd_decoder_best_path_prepare / _fetch; any may be NULL,
  * arrays must hold *num_lanes entries (at most the n of the call). */

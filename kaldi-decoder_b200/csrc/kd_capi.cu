@@ -1079,10 +1079,24 @@ int kd_decoder_advance_async(kd_decoder *d, int32_t n, const int32_t *lanes,
   if (work.empty()) return KD_OK;
   const int32_t m = static_cast<int32_t>(work.size());
 
-  // a free slot; if all are in flight the oldest completes first
-  int si = -1;
-  for (int i = 0; i < kNumSlots; ++i)
-    if (!d->slots[i].busy && (si < 0 || d->slots[i].ticket < d->slots[si].ticket)) si = i;
+  // A free slot.  Slots that have been used before keep their staging and result buffers:
+  // they are taken in turn (least recently used first, so the results of a call stay readable
+  // for at least the next two calls); a fresh slot is only opened when every used one is in
+  // flight (or fewer than three are in use).  If all are in flight the oldest completes first.
+  int si = -1, n_used = 0;
+  for (int i = 0; i < kNumSlots; ++i) {
+    if (d->slots[i].ticket >= 0) ++n_used;
+    if (!d->slots[i].busy && d->slots[i].ticket >= 0 &&
+        (si < 0 || d->slots[i].ticket < d->slots[si].ticket))
+      si = i;
+  }
+  if (si < 0 || n_used < 3) {
+    for (int i = 0; i < kNumSlots; ++i)
+      if (d->slots[i].ticket < 0) {
+        si = i;
+        break;
+      }
+  }
   if (si < 0) {
     for (int i = 0; i < kNumSlots; ++i)
       if (si < 0 || d->slots[i].ticket < d->slots[si].ticket) si = i;

@@ -77,8 +77,14 @@ constexpr int kOrderBins = 512;           // buckets of the per-frame label orde
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
 // 32-item windows a warp takes per scan step.  2 or 3 (more loads in flight per warp) make
 // the scan 5% faster and the other phases slower by as much (code size, registers).
-constexpr int kWin = 1;
-constexpr int kTileTokens = 2;            // tokens per thread in one scan tile
+#ifndef KD_WIN
+#define KD_WIN 1
+#endif
+constexpr int kWin = KD_WIN;
+#ifndef KD_TILE_TOKENS
+#define KD_TILE_TOKENS 2
+#endif
+constexpr int kTileTokens = KD_TILE_TOKENS;  // tokens per thread in one scan tile
 constexpr int kListSmem = KD_OPT_SLIST ? 1024 : 0;  // slot-list entries kept in shared memory
 constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones

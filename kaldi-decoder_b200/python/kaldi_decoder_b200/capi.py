@@ -339,7 +339,7 @@ class LaneDecoder:
 
     def results(self, ticket: int, use_final_probs: bool = True, copy: bool = True) -> "PathBatch":
         """Best paths of a finalize=True call.  copy=False returns views of the decoder's
-        pinned result buffer (valid until the 16th-next advance_async call)."""
+        pinned result buffer (valid until the third-next advance_async call)."""
         n = C.c_int32(0)
         lp, wp, op = C.c_void_p(), C.c_void_p(), C.c_void_p()
         cap = self.max_lanes
