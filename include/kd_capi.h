@@ -63,10 +63,16 @@ typedef struct kd_decoder_config {
   int32_t max_lanes;        /* number of utterance lanes (default 1)                   */
   int32_t hash_capacity;    /* per-lane recombination-table entries, power of two;
                                tokens alive in one frame must stay <= capacity / 2     */
-  int64_t arena_records;    /* per-lane backpointer-store records (sum over frames of
-                               tokens alive at frame end), 20 bytes each               */
+  int64_t arena_records;    /* per-lane backpointer-store records, 20 bytes each.  The store
+                               is garbage-collected on the device when it fills up (the
+                               reference frees dead tokens by reference counting,
+                               faster-decoder.h:145-155): it has to hold the tokens still
+                               reachable from the live ones plus the current frame, not the
+                               sum over all frames                                     */
   int32_t threads_per_lane; /* 128/160/192/224/256/384/512; default: the widest
-                               that keeps all lanes of a call resident at once         */
+                               that keeps all lanes of a call resident at once (160 with
+                               7 lanes per SM is the best when the chip is kept full by
+                               several calls in flight)                                */
   int32_t chunk_frames;     /* host-memory advance: frames per copy/search pipeline
                                stage (default 128)                                     */
   int32_t search;           /* KD_SEARCH_FASTER (default) or KD_SEARCH_SIMPLE          */

@@ -1840,6 +1840,17 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
     if (tid == 0) sh.item = atomicAdd(P.work_counter, 1);
     __syncthreads();
     const int item = sh.item;
+    // a lane that stopped on an error may have left the bulk copy of its next row in flight:
+    // it is drained before the row buffer gets a new owner (or the CTA exits)
+    if (sh.row_pending != 0) {
+      mbar_wait(&sh.row_bar, sh.row_parity);
+      __syncthreads();
+      if (tid == 0) {
+        sh.row_parity ^= 1u;
+        sh.row_pending = 0;
+      }
+      __syncthreads();
+    }
     if (item >= P.n_items) return;
     const AdvanceItem it = P.items[item];
     // InitDecoding in the same launch: the first pass of the loop below has no emitting

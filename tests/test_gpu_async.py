@@ -240,3 +240,45 @@ def test_epsilon_ties_are_resolved_deterministically(seed):
         pb = dec.decode(lanes, mats, True)
         for u in lanes:
             assert _same_raw(pb[u], want[u]), (seed, rnd, u)
+
+
+def test_lane_error_does_not_leak_its_prefetched_row_into_the_next_lane():
+    """More lanes than CTA slots: a CTA whose lane stops on an overflow (with the bulk copy
+    of its next row already in flight) goes on to another lane, which must start from its
+    own first row."""
+    g = small_graph("HL")
+    opts = dict(beam=12.0, max_active=2**31 - 1, min_active=0)
+    n, T = 1300, 24
+    V = int(g.lm["vocab"])
+    good = [synth.make_logprobs(g, T, seed=900 + u, peak=9) for u in range(8)]
+    og = kd_oracle.OracleGraph(g)
+    want = []
+    for m in good:
+        o = kd_oracle.OracleDecoder(og, kd_ref.Options(**opts), kd_oracle.CANONICAL)
+        o.decode(m)
+        want.append((sorted_tokens(*o.tokens()), o.stats()["max_tokens"]))
+    cap = 1 << 13
+    assert max(w[1] for w in want) < cap // 16
+    flat = np.full((T, V), np.float32(-np.log(V)), dtype=np.float32)  # every arc survives
+    flat[:, :] += (np.arange(V, dtype=np.float32) * np.float32(1e-4))[None, :]
+    o = kd_oracle.OracleDecoder(og, kd_ref.Options(**opts), kd_oracle.CANONICAL)
+    o.decode(flat[:6])
+    assert o.stats()["max_tokens"] > cap  # the flat lanes do overflow the table (capacity / 2 tokens)
+    bad = {u for u in range(n) if u < 1100 and u % 3 == 0}
+    mats = [flat if u in bad else good[u % len(good)] for u in range(n)]
+    dg = capi.DeviceGraph.from_graph(g)
+    dec = capi.LaneDecoder(dg, capi.make_options(**opts), max_lanes=n, hash_capacity=cap,
+                           arena_records=1 << 15, threads_per_lane=160)
+    lanes = list(range(n))
+    with pytest.raises(capi.KdError, match="overflow"):
+        dec.decode(lanes, mats, True)
+    for u in lanes:
+        if u in bad:
+            continue
+        assert dec.num_frames_decoded(u) == T, u
+        gs, gc = sorted_tokens(*dec.tokens(u))
+        (os_, oc), _ = want[u % len(good)]
+        assert np.array_equal(gs, os_) and np.array_equal(gc, oc), u
+    for u in sorted(bad)[:5]:
+        with pytest.raises(capi.KdError):
+            dec.tokens(u) if dec.num_frames_decoded(u) == T else dec.advance([u], [flat])
