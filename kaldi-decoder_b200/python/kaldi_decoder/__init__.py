@@ -95,6 +95,8 @@ def _cuda_matrices(tensors):
                 # the stream the tensors were (or are being) produced on: the search is ordered
                 # behind it -- the decoder's own streams do not synchronise with torch's
                 stream = int(torch.cuda.current_stream(t.device).cuda_stream)
+        elif not hasattr(t, "__cuda_array_interface__") and hasattr(t, "__dlpack__"):
+            ptr, shape, dev = _from_dlpack(t)
         else:
             cai = t.__cuda_array_interface__
             if cai["typestr"] not in ("<f4", "=f4") or len(cai["shape"]) != 2 or cai.get("strides"):
@@ -117,12 +119,58 @@ def _cuda_matrices(tensors):
     return ptrs, rows, int(cols or 0), stream, device
 
 
+def _from_dlpack(t):
+    """(data pointer, shape, device index) of a DLPack exporter holding a compact float32
+    [T, V] CUDA matrix.  The capsule is consumed (its deleter runs here); the exporter `t`
+    keeps the memory alive, so `t` has to outlive the decoding call -- as for every other
+    accepted array type."""
+    import ctypes as C
+
+    class DLDevice(C.Structure):
+        _fields_ = [("device_type", C.c_int), ("device_id", C.c_int)]
+
+    class DLDataType(C.Structure):
+        _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+    class DLTensor(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("device", DLDevice), ("ndim", C.c_int),
+                    ("dtype", DLDataType), ("shape", C.POINTER(C.c_int64)),
+                    ("strides", C.POINTER(C.c_int64)), ("byte_offset", C.c_uint64)]
+
+    class DLManagedTensor(C.Structure):
+        pass
+
+    DLManagedTensor._fields_ = [("dl_tensor", DLTensor), ("manager_ctx", C.c_void_p),
+                                ("deleter", C.CFUNCTYPE(None, C.POINTER(DLManagedTensor)))]
+    cap = t.__dlpack__()
+    api = C.pythonapi
+    api.PyCapsule_GetPointer.restype = C.c_void_p
+    api.PyCapsule_GetPointer.argtypes = [C.py_object, C.c_char_p]
+    api.PyCapsule_SetName.argtypes = [C.py_object, C.c_char_p]
+    mt = C.cast(api.PyCapsule_GetPointer(cap, b"dltensor"), C.POINTER(DLManagedTensor))
+    d = mt.contents.dl_tensor
+    try:
+        kDLCUDA, kDLFloat = 2, 2
+        if d.device.device_type != kDLCUDA:
+            raise ValueError("expected a CUDA array (DLPack device type kDLCUDA)")
+        if (d.dtype.code, d.dtype.bits, d.dtype.lanes) != (kDLFloat, 32, 1) or d.ndim != 2:
+            raise ValueError("expected a float32 [T, V] array")
+        shape = (int(d.shape[0]), int(d.shape[1]))
+        if d.strides and shape[0] > 0 and (int(d.strides[1]) != 1 or int(d.strides[0]) != shape[1]):
+            raise ValueError("expected a compact row-major array")
+        return int(d.data or 0) + int(d.byte_offset), shape, int(d.device.device_id)
+    finally:
+        api.PyCapsule_SetName(cap, b"used_dltensor")  # consumed: the capsule must not free it again
+        if mt.contents.deleter:
+            mt.contents.deleter(mt)
+
+
 def advance_decoding_cuda(decoder: "BatchFasterDecoder", lanes, tensors, offsets=None,
                           max_num_frames: int = -1, device: int = None) -> None:
     """`BatchFasterDecoder.advance_decoding` for log-probs that already live on the GPU.
 
     `tensors[i]` is a contiguous float32 `[T_i, V]` CUDA array for lane `lanes[i]`: a torch
-    tensor, or anything exposing `__cuda_array_interface__` (CuPy, Numba).  No copy is made and
+    tensor, anything exposing `__cuda_array_interface__` (CuPy, Numba) or `__dlpack__`.  No copy is made and
     the call returns when the frames are decoded, so the arrays only have to outlive the call.
 
     Stream ordering: the decoder launches on its own non-blocking streams.  For torch tensors

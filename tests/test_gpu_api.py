@@ -406,5 +406,24 @@ def test_const_fst_overload_and_deferred_batches_through_the_python_package():
     for u in range(n):
         assert kd.get_linear_symbol_sequence(lats[u])[2] == [int(x) for x in gc.best(u).osyms]
     kd.advance_decoding_cuda(bd, [0], [dev[0][:0]], offsets=[rows[0]], device=0)  # nothing new: a no-op
+
+    class OnlyDLPack:  # a foreign CUDA array that speaks DLPack and nothing else
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    wrapped = [OnlyDLPack(x) for x in dev]
+    torch.cuda.synchronize()
+    t = kd.decode_cuda_async(bd, list(range(n)), wrapped)
+    lanes, oks, lats = bd.get_results(t)
+    for u in range(n):
+        assert kd.get_linear_symbol_sequence(lats[u])[2] == [int(x) for x in gc.best(u).osyms]
+    with pytest.raises(ValueError):
+        kd.decode_cuda_async(bd, [0], [OnlyDLPack(dev[0].double())])
     with pytest.raises(ValueError):
         kd.advance_decoding_cuda(bd, [0], [dev[0]], device=1)

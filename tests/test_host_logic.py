@@ -332,3 +332,23 @@ def test_host_sources_compile_against_an_openfst_shaped_fst_h(tmp_path):
     r = subprocess.run([cxx, "-std=c++17", "-fsyntax-only", *inc, str(bad)], capture_output=True,
                        text=True)
     assert r.returncode != 0 and "NumStates" in r.stderr
+
+
+def test_dlpack_ingest_parses_the_capsule_and_rejects_host_arrays():
+    """kaldi_decoder._from_dlpack: the DLManagedTensor is read through ctypes, the capsule is
+    consumed exactly once (no double free when the capsule object dies afterwards)."""
+    torch = pytest.importorskip("torch")
+    import gc
+    import kaldi_decoder as kd
+
+    class W:
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__()
+
+    for _ in range(50):
+        with pytest.raises(ValueError, match="CUDA"):
+            kd._from_dlpack(W(torch.zeros(3, 4)))
+    gc.collect()
