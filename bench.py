@@ -47,6 +47,10 @@ for p in (ROOT, os.path.join(ROOT, "kaldi-decoder_b200", "python")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# many calls in flight need more hardware queues than the default 8 (see kd_capi.cu); the
+# variable must be set before the CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np  # noqa: E402
 
 METRIC = "decoded_frames_per_sec"

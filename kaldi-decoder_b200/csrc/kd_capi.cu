@@ -48,6 +48,15 @@ int DevAlloc(T **p, size_t n) {
   return KD_OK;
 }
 
+// Calls in flight run on up to 2 x kNumSlots streams.  The driver maps streams onto
+// CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams sharing a queue serialise:
+// a call's copy stream stuck behind another call's persistent search kernel starves its own
+// lanes.  The variable is read when the CUDA context is created, so it is set (if the
+// application has not chosen a value) as soon as this library is loaded.
+__attribute__((constructor)) void KdRaiseMaxConnections() {
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", /*overwrite=*/0);
+}
+
 }  // namespace
 
 struct kd_graph {
@@ -277,9 +286,14 @@ int LaunchAdvance(kd_decoder *d, const kd::Params &P, int n_items, int threads,
   // (second template argument: lanes per SM the register budget is cut for -- the measured
   // best per thread count: profiles/r2_sweeps.txt)
 #ifdef KD_ONLY_160
-  // (quick A/B builds: one instantiation)
-  if (threads != 160) return Fail(KD_ERR_INVALID, "this build only has 160-thread lanes");
-  return LaunchAdvanceT<160, 7>(d, P, n_items, s);
+  // (quick A/B builds: one instantiation, -DKD_AB_THREADS=t -DKD_AB_BLOCKS=b to pick another)
+#ifndef KD_AB_THREADS
+#define KD_AB_THREADS 160
+#define KD_AB_BLOCKS 7
+#endif
+  if (threads != KD_AB_THREADS && threads != 160)
+    return Fail(KD_ERR_INVALID, "this build has one lane width only");
+  return LaunchAdvanceT<KD_AB_THREADS, KD_AB_BLOCKS>(d, P, n_items, s);
 #else
   switch (threads) {
     case 128:

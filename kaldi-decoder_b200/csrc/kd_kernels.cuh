@@ -61,7 +61,9 @@ constexpr int kStatusHashOverflow = 1;
 constexpr int kStatusArenaOverflow = 2;
 constexpr int kStatusQueueOverflow = 4;
 constexpr int kStatusInputStall = 8;  // streamed log-probs never arrived (set by the host)
-constexpr long long kYieldCycles = 40000000;  // ~20 ms of polling before a lane yields
+// ~1 s of polling before a lane yields.  (Long on purpose: with many calls in flight a call's
+// rows queue behind the other calls' copies for tens of milliseconds.)
+constexpr long long kYieldCycles = 2000000000ll;
 constexpr int kStatusCandOverflow = 16;  // SimpleDecoder search: candidate buffer full
 
 // In an arc field: "epsilon arc".  In a nextstate field: "state has epsilon arcs".
@@ -1892,7 +1894,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
             int32_t ready = *pr;
             const long long t0 = clock64();
             while (ready <= frame - it.offset) {
-              // Nothing for ~20 ms: the copies are not coming while this kernel runs
+              // Nothing for ~1 s: the copies are not coming while this kernel runs
               // (launches are serialised -- CUDA_LAUNCH_BLOCKING, a profiler -- or the host
               // is staging pageable memory).  The lane yields: its state is saved as it is
               // and the host launches again once the copies are enqueued.
