@@ -51,6 +51,9 @@
 #ifndef KD_OPT_SINGLE_PASS
 #define KD_OPT_SINGLE_PASS 1  // token blocks of at most one scan tile are scanned in one pass
 #endif
+#ifndef KD_OPT_CAND_CACHED
+#define KD_OPT_CAND_CACHED 0  // candidate buffer / front list with default (write-back) caching instead of streaming
+#endif
 #ifndef KD_OPT_SLIST
 #define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
 #endif
@@ -1328,7 +1331,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         ti[k] = i;
         if (i < tile_end) {
           if (front_list) {
-            const uint4 rec = __ldcs(B.front + i);
+            const uint4 rec = KD_OPT_CAND_CACHED ? __ldcg(B.front + i) : __ldcs(B.front + i);
             tc[k] = dunkey((static_cast<unsigned long long>(rec.y) << 32) | rec.x);
             ts[k] = static_cast<int32_t>(rec.z);
             ti[k] = rec.w;
@@ -1505,8 +1508,13 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
             const unsigned long long nk = dkey(nw);
             const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
             if (e < P.ccap) {
-              __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
+              if (KD_OPT_CAND_CACHED) {
+                B.cand[e] = make_uint4(static_cast<uint32_t>(nk),
+                                            static_cast<uint32_t>(nk >> 32), aa[u], tok_abs);
+              } else {
+                __stcs(B.cand + e, make_uint4(static_cast<uint32_t>(nk),
                                             static_cast<uint32_t>(nk >> 32), aa[u], tok_abs));
+              }
             } else if (SIMPLE) {
               atomicOr(&sh.status, kStatusCandOverflow);
             } else {
@@ -1546,7 +1554,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // lanes slower by as much; claiming the slot with the CAS before any probe load.)
   double min_stored = inf;  // SIMPLE only
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
-    const uint4 c = __ldcs(B.cand + e);
+    const uint4 c = KD_OPT_CAND_CACHED ? __ldcg(B.cand + e) : __ldcs(B.cand + e);
     unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
     if (!(nk < cstar_key)) continue;  // faster-decoder.cc:211 / simple-decoder.cc:170, final cutoff
     if (SIMPLE) {
