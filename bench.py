@@ -391,6 +391,9 @@ def main():
         e2e = {"value": frames_per_step / (dt_h / args.steps), "unit": UNIT,
                "h2d_bytes_per_step": int(lanes * T * V * 4), "d2h_bytes_per_step": d2h,
                "ms_per_step": dt_h / args.steps * 1e3,
+               # what every rank's host link has to sustain; with several ranks uploading at
+               # once this, not the search, bounds the end-to-end figure
+               "h2d_gb_per_s_per_rank": lanes * T * V * 4 / (dt_h / args.steps) / 1e9,
                "kernel_span_ms_per_step": span_h / max(1, n_launch_h)}
 
     cpu = None
