@@ -283,19 +283,28 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
            }),
            py::arg("graph"), py::arg("config"), py::arg("device_config") = DeviceConfig())
       .def("set_options", &FasterDecoder::SetOptions, py::arg("config"))
-      .def("decode", &FasterDecoder::Decode, py::arg("decodable"))
-      .def("reached_final", &FasterDecoder::ReachedFinal)
+      // The GIL is released while the device works (the reference holds it for the whole
+      // search): decoders driven from several Python threads -- one FasterDecoder per thread
+      // on a shared DeviceGraph -- run their searches concurrently on the GPU.  A decodable
+      // defined in Python re-acquires it inside its callbacks (pybind11 trampolines).
+      .def("decode", &FasterDecoder::Decode, py::arg("decodable"),
+           py::call_guard<py::gil_scoped_release>())
+      .def("reached_final", &FasterDecoder::ReachedFinal, py::call_guard<py::gil_scoped_release>())
       .def(
           "get_best_path",
           [](FasterDecoder &self, bool use_final_probs) -> std::pair<bool, fst::Lattice> {
             fst::Lattice lat;
-            bool ok = self.GetBestPath(&lat, use_final_probs);
+            bool ok;
+            {
+              py::gil_scoped_release nogil;
+              ok = self.GetBestPath(&lat, use_final_probs);
+            }
             return std::make_pair(ok, lat);
           },
           py::arg("use_final_probs") = true)
-      .def("init_decoding", &FasterDecoder::InitDecoding)
+      .def("init_decoding", &FasterDecoder::InitDecoding, py::call_guard<py::gil_scoped_release>())
       .def("advance_decoding", &FasterDecoder::AdvanceDecoding, py::arg("decodable"),
-           py::arg("max_num_frames") = -1)
+           py::arg("max_num_frames") = -1, py::call_guard<py::gil_scoped_release>())
       .def("num_frames_decoded", &FasterDecoder::NumFramesDecoded);
 
   // ---- SimpleDecoder (kaldi-decoder/python/csrc/simple-decoder.cc:14-44)

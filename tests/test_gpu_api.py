@@ -427,3 +427,39 @@ def test_const_fst_overload_and_deferred_batches_through_the_python_package():
         kd.decode_cuda_async(bd, [0], [OnlyDLPack(dev[0].double())])
     with pytest.raises(ValueError):
         kd.advance_decoding_cuda(bd, [0], [dev[0]], device=1)
+
+
+def test_single_utterance_decoders_run_concurrently_from_python_threads():
+    """One FasterDecoder per thread on a shared DeviceGraph: the bindings release the GIL while
+    the device works, every decoder owns its lane and streams; results are the reference's."""
+    import threading
+    import kaldi_decoder as kd
+    gc = GoldenCase("hlg300_peaky")
+    g = gc.graph
+    o = gc.opts
+    fst = kd.StdConstFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                     g.weight, g.nextstate, g.final)
+    graph = kd.DeviceGraph(fst)
+    opts = kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"], min_active=o["min_active"])
+    n_threads = 4
+    errors = []
+
+    def work(k):
+        try:
+            dec = kd.FasterDecoder(graph, opts)
+            for rep in range(6):
+                u = (k + rep) % gc.n_utts
+                dec.decode(kd.DecodableCtc(gc.logp(u)))
+                ok, best = dec.get_best_path()
+                want = gc.best(u, True)
+                assert ok == want.ok and dec.reached_final() == gc.reached_final(u)
+                assert kd.get_linear_symbol_sequence(best)[2] == [int(x) for x in want.osyms]
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
