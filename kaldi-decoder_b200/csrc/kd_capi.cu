@@ -128,6 +128,7 @@ struct kd_decoder {
   unsigned long long *a_link = nullptr;
   int32_t *a_state = nullptr;
   kd::Entry *table = nullptr;
+  uint32_t *bitmap = nullptr;  // hcap / 32 words per lane: table entries in use
   uint32_t *list = nullptr;
   uint2 *queue = nullptr;
   uint4 *cand = nullptr;
@@ -206,6 +207,7 @@ kd::Params MakeParams(const kd_decoder *d) {
   P.a_state = d->a_state;
   P.arena_cap = d->arena_cap;
   P.table = d->table;
+  P.bitmap = d->bitmap;
   P.list = d->list;
   P.queue = d->queue;
   P.cand = d->cand;
@@ -645,7 +647,8 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   const size_t A = static_cast<size_t>(d->arena_cap);
   if ((rc = DevAlloc(&d->lanes, L)) || (rc = DevAlloc(&d->a_cost, L * A)) ||
       (rc = DevAlloc(&d->a_link, L * A)) || (rc = DevAlloc(&d->a_state, L * A)) ||
-      (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->list, L * d->lcap)) ||
+      (rc = DevAlloc(&d->table, L * d->hcap)) || (rc = DevAlloc(&d->bitmap, L * (d->hcap / 32))) ||
+      (rc = DevAlloc(&d->list, L * d->lcap)) ||
       (rc = DevAlloc(&d->queue, L * 2 * d->qcap)) || (rc = DevAlloc(&d->cand, L * d->ccap)) ||
       (rc = DevAlloc(&d->front, L * kd::kFrontCap)) || (rc = DevAlloc(&d->d_items, L)) ||
       (rc = DevAlloc(&d->d_out_off, L)) || (rc = DevAlloc(&d->d_flags, L)))
@@ -653,6 +656,7 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->device_bytes = L * (sizeof(kd::LaneState) + A * 20 + table_bytes_per_lane);
   KD_CUDA_D(cudaMemset(d->lanes, 0, L * sizeof(kd::LaneState)));
   KD_CUDA_D(cudaMemset(d->table, 0xFF, L * d->hcap * sizeof(kd::Entry)));
+  KD_CUDA_D(cudaMemset(d->bitmap, 0, L * (d->hcap / 32) * sizeof(uint32_t)));
   KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_items), L * sizeof(kd::AdvanceItem)));
   KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_lanes), L * sizeof(kd::LaneState)));
   KD_CUDA_D(cudaMallocHost(reinterpret_cast<void **>(&d->h_out_off), L * sizeof(long long)));
@@ -719,6 +723,7 @@ int kd_decoder_destroy(kd_decoder *d) {
   cudaFree(d->a_link);
   cudaFree(d->a_state);
   cudaFree(d->table);
+  cudaFree(d->bitmap);
   cudaFree(d->list);
   cudaFree(d->queue);
   cudaFree(d->cand);
@@ -999,6 +1004,7 @@ int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
       // a lane that overflowed may have left claimed table slots behind
       size_t off = static_cast<size_t>(lane) * d->hcap;
       KD_CUDA(cudaMemsetAsync(d->table + off, 0xFF, d->hcap * sizeof(kd::Entry), s));
+      KD_CUDA(cudaMemsetAsync(d->bitmap + off / 32, 0, d->hcap / 8, s));
       d->status[lane] = 0;
     }
     memset(&d->h_items[i], 0, sizeof(kd::AdvanceItem));
@@ -1184,6 +1190,8 @@ int kd_decoder_advance_async(kd_decoder *d, int32_t n, const int32_t *lanes,
       // a lane that overflowed may have left claimed table slots behind
       KD_CUDA(cudaMemsetAsync(d->table + static_cast<size_t>(lane) * d->hcap, 0xFF,
                               d->hcap * sizeof(kd::Entry), s.sc));
+      KD_CUDA(cudaMemsetAsync(d->bitmap + static_cast<size_t>(lane) * (d->hcap / 32), 0,
+                              d->hcap / 8, s.sc));
       d->status[lane] = 0;
     }
   }

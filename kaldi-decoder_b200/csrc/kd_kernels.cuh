@@ -104,12 +104,25 @@ struct __align__(16) HVal {
 // sector (the first layout used three arrays = three sectors per state and
 // thrashed L2: profiles/r1_v0_ncu_summary.txt).
 struct __align__(32) Entry {
-  HVal val;       // 16-byte aligned: target of the 128-bit CAS
-  int32_t key;    // state id, kEmptyKey when free
-  uint32_t idx;   // position in this frame's slot list = index of the token in the next block
-  uint32_t pad[2];
+  HVal val;        // 16-byte aligned: target of the 128-bit CAS
+  int32_t key;     // state id
+  uint32_t idx;    // position in this frame's slot list = index of the token in the next block
+  uint32_t epoch;  // the lane-frame that wrote the entry: any other value = stale contents
+  uint32_t pad;
 };
 
+// Which entries are in use is kept in a per-lane BITMAP (one bit per entry), not in the
+// entries: claiming an entry is one atomicOr on a word that lives in L2 (32 KB per lane at
+// 2^18 entries, re-used every frame), and the thread that flips the bit writes the whole
+// 32-byte entry -- key, slot-list position, epoch and ITS OWN value -- with one 256-bit store
+// (STG.256: a full sector, so L2 does not fetch the old contents from DRAM).  The first
+// arrival at a state, 80 % of all arrivals, thus costs one L2 round trip; before, it cost a
+// probe load that missed to DRAM (the table is 8 MB per lane), a CAS on the key and a CAS on
+// the value.  Entries are never wiped: the commit clears the bits, and a later arrival that
+// finds a bit set validates the entry by its epoch (a thread that finds the bit set before
+// the owner's store has landed re-reads until it has).
+
+// Everything the device keeps per lane between calls.
 // Everything the device keeps per lane between calls.
 struct __align__(16) LaneState {
   int32_t n_tok;           // records in the current token block (n_live tokens + dead records)
@@ -132,6 +145,8 @@ struct __align__(16) LaneState {
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit, cyc_scan;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
   long long st_compactions;  // arena garbage collections
+  uint32_t epoch;          // stamps the table entries of the current pass; survives InitDecoding
+  uint32_t pad0;
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
   long long st_items;    // arcs actually evaluated (scanned + looked up)
   // best-path selection results
@@ -187,6 +202,7 @@ struct Params {
   int32_t *a_state;
   long long arena_cap;
   Entry *table;
+  uint32_t *bitmap;  // hcap / 32 words per lane: entries in use
   uint32_t *list;
   uint2 *queue;     // 2 * qcap per lane: {table slot, state}
   uint4 *cand;      // ccap per lane: arcs that passed the running-cutoff filter
@@ -247,24 +263,45 @@ __device__ __forceinline__ unsigned long long l2_evict_last() {
 }
 
 // ---- recombination-table accesses
+struct EntryWords {  // one entry as loaded by a 256-bit load
+  HVal val;
+  int32_t key;
+  uint32_t idx;
+  uint32_t epoch;
+};
+
+__device__ __forceinline__ EntryWords ld_entry(const Entry *e) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.cg.v4.b64 {%0, %1, %2, %3}, [%4];"
+               : "=l"(a), "=l"(b), "=l"(c), "=l"(d)
+               : "l"(e)
+               : "memory");
+  EntryWords w;
+  w.val.cost = a;
+  w.val.arg = b;
+  w.key = static_cast<int32_t>(c);
+  w.idx = static_cast<uint32_t>(c >> 32);
+  w.epoch = static_cast<uint32_t>(d);
+  return w;
+}
+
+__device__ __forceinline__ void st_entry(Entry *e, HVal v, int32_t key, uint32_t idx,
+                                         uint32_t epoch) {
+  const unsigned long long c =
+      static_cast<unsigned long long>(static_cast<uint32_t>(key)) |
+      (static_cast<unsigned long long>(idx) << 32);
+  const unsigned long long d = epoch;
+  asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(e), "l"(v.cost), "l"(v.arg),
+               "l"(c), "l"(d)
+               : "memory");
+}
+
 __device__ __forceinline__ HVal ld_hval(const HVal *p) {
   HVal r;
   ulonglong2 v = __ldcg(reinterpret_cast<const ulonglong2 *>(p));
   r.cost = v.x;
   r.arg = v.y;
   return r;
-}
-__device__ __forceinline__ int32_t ld_key(const int32_t *p) { return __ldcg(p); }
-__device__ __forceinline__ int2 ld_key_idx(const int32_t *p) {
-  return __ldcg(reinterpret_cast<const int2 *>(p));
-}
-// wipes an entry (value and key)
-__device__ __forceinline__ void st_wipe(Entry *e) {
-  ulonglong2 v;
-  v.x = kEmptyCost;
-  v.y = kEmptyArg;
-  *reinterpret_cast<ulonglong2 *>(&e->val) = v;
-  e->key = kEmptyKey;
 }
 
 // ---- graph loads (read-only path)
@@ -474,6 +511,7 @@ struct LaneBuf {
   unsigned long long *a_link;
   int32_t *a_state;
   Entry *table;
+  uint32_t *bitmap;
   uint32_t *list;
   uint2 *queue;
   uint4 *cand;
@@ -488,6 +526,7 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   b.a_link = P.a_link + L * P.arena_cap;
   b.a_state = P.a_state + L * P.arena_cap;
   b.table = P.table + L * P.hcap;
+  b.bitmap = P.bitmap + L * (P.hcap >> 5);
   b.list = P.list + L * P.lcap;
   b.queue = P.queue + L * 2 * P.qcap;
   b.cand = P.cand + L * P.ccap;
@@ -495,12 +534,18 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   return b;
 }
 
+__device__ __forceinline__ uint32_t table_hash(const Params &P, int32_t state) {
+  // groups of 4 consecutive states share a 128-byte line; groups are scattered
+  return ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
+         (static_cast<uint32_t>(state) & 3u);
+}
+
 // A slot that was just claimed joins this frame's slot list (its position there is the
-// token's number in the next block) and, when `eps_queue` is given (the state has
-// epsilon arcs), that queue: the closure only visits those.
-__device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B, Shared &sh,
-                                               uint32_t h, int32_t state, uint2 *eps_queue,
-                                               uint32_t *eps_queue_n) {
+// token's number in the next block: the return value) and, when `eps_queue` is given (the
+// state has epsilon arcs), that queue: the closure only visits those.
+__device__ __forceinline__ uint32_t register_claim(const Params &P, const LaneBuf &B, Shared &sh,
+                                                   uint32_t h, int32_t state, uint2 *eps_queue,
+                                                   uint32_t *eps_queue_n) {
   const uint32_t pos = atomicAdd(&sh.list_n, 1u);
   if (pos < P.lcap) {
     if (pos < static_cast<uint32_t>(kListSmem)) {
@@ -508,7 +553,6 @@ __device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B
     } else {
       B.list[pos] = h;
     }
-    B.table[h].idx = pos;  // tokens are numbered in claim order
   } else {
     atomicOr(&sh.status, kStatusHashOverflow);
   }
@@ -520,48 +564,48 @@ __device__ __forceinline__ void register_claim(const Params &P, const LaneBuf &B
       atomicOr(&sh.status, kStatusQueueOverflow);
     }
   }
+  return pos;
 }
 
-// Finds the table slot of `state`, claiming an empty one if needed.  Probes are
-// plain loads; an atomic is spent only on an empty slot.  (Probing with the
-// CAS itself saves a round trip for new states but turns every arrival at an
-// existing state into an L2 atomic: measured slower, profiles/r1_v5_*.)  A
-// newly claimed slot is appended to this frame's slot list and, when
-// `eps_queue` is given (the state has epsilon arcs), to that queue: the
-// closure only visits those.  Returns kNoIdx on overflow.
-__device__ __forceinline__ uint32_t table_slot_from(const Params &P, const LaneBuf &B,
-                                                    Shared &sh, int32_t state, uint32_t h,
-                                                    int32_t k, uint2 *eps_queue,
-                                                    uint32_t *eps_queue_n) {
-  // `k` is the key already loaded from slot `h` (the first probe)
+// The arrival `mine` at `state`.  Returns the state's slot, or kNoIdx on overflow.
+//   *owner = true : the state was not in the table; this thread took an entry for it and has
+//                   written it, value included -- nothing else to do;
+//   *owner = false: the state has an entry; *cur is its value as just read (the caller
+//                   recombines with a CAS on Entry::val).
+// Probing is linear over the bitmap: the first entry of the probe sequence whose bit this
+// thread flips is its own; an entry whose bit was already set belongs to the state it names.
+__device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf &B, Shared &sh,
+                                                 uint32_t epoch, int32_t state, HVal mine,
+                                                 uint2 *eps_queue, uint32_t *eps_queue_n,
+                                                 bool *owner, HVal *cur) {
+  uint32_t h = table_hash(P, state);
   for (uint32_t probe = 0; probe < P.hcap; ++probe) {
-    if (k == state) return h;
-    if (k == kEmptyKey) {
-      k = atomicCAS(&B.table[h].key, kEmptyKey, state);
-      if (k == state) return h;
-      if (k == kEmptyKey) {
-        register_claim(P, B, sh, h, state, eps_queue, eps_queue_n);
-        return h;
+    const uint32_t bit = 1u << (h & 31u);
+    const uint32_t old = atomicOr(B.bitmap + (h >> 5), bit);
+    if ((old & bit) == 0) {
+      const uint32_t pos = register_claim(P, B, sh, h, state, eps_queue, eps_queue_n);
+      st_entry(B.table + h, mine, state, pos, epoch);
+      *owner = true;
+      return h;
+    }
+    // in use: by whom?  (its owner's store may still be on its way: the epoch tells)
+    EntryWords w = ld_entry(B.table + h);
+    for (uint32_t spins = 0; w.epoch != epoch; ++spins) {
+      if (spins > (1u << 22)) {  // never in a correct run: fail instead of hanging
+        atomicOr(&sh.status, kStatusHashOverflow);
+        return kNoIdx;
       }
+      w = ld_entry(B.table + h);
+    }
+    if (w.key == state) {
+      *owner = false;
+      *cur = w.val;
+      return h;
     }
     h = (h + 1) & P.hmask;
-    k = ld_key(&B.table[h].key);
   }
   atomicOr(&sh.status, kStatusHashOverflow);
   return kNoIdx;
-}
-
-__device__ __forceinline__ uint32_t table_hash(const Params &P, int32_t state) {
-  // groups of 4 consecutive states share a 128-byte line; groups are scattered
-  return ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
-         (static_cast<uint32_t>(state) & 3u);
-}
-
-__device__ __forceinline__ uint32_t table_slot(const Params &P, const LaneBuf &B, Shared &sh,
-                                               int32_t state, uint2 *eps_queue,
-                                               uint32_t *eps_queue_n) {
-  const uint32_t h = table_hash(P, state);
-  return table_slot_from(P, B, sh, state, h, ld_key(&B.table[h].key), eps_queue, eps_queue_n);
 }
 
 // Block-wide count of tokens with float(cost) <= bound (used to skip the exact
@@ -688,42 +732,37 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, const La
 // has epsilon arcs (flag in the arc's nextstate word).
 template <bool SIMPLE>
 __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
-                                            uint32_t dst_word, unsigned long long cost_key,
-                                            uint32_t arc, uint32_t src_number,
-                                            unsigned long long cstar_key, uint2 *q_next,
-                                            uint32_t *q_next_n) {
-  // key and value of the first probed slot are fetched together (one sector, one round trip)
+                                            uint32_t epoch, uint32_t dst_word,
+                                            unsigned long long cost_key, uint32_t arc,
+                                            uint32_t src_number, unsigned long long cstar_key,
+                                            uint2 *q_next, uint32_t *q_next_n) {
   const int32_t state = static_cast<int32_t>(dst_word & ~kEpsFlag);
-  const uint32_t h0 = table_hash(P, state);
-  const int32_t k0 = ld_key(&B.table[h0].key);
-  HVal cur = ld_hval(&B.table[h0].val);
-  uint32_t h = h0;
-  if (k0 != state) {
-    h = table_slot_from(P, B, sh, state, h0, k0, nullptr, nullptr);
-    if (h == kNoIdx) return;
-    // a freshly claimed slot holds the empty value; a slot found further along is re-read
-    if (h != h0 || k0 != kEmptyKey) cur = ld_hval(&B.table[h].val);
-  }
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_number;
-  bool tie_only;
-  while (true) {
-    const bool cur_is_eps = (cur.arg >> 63) != 0;
-    // Two epsilon arrivals with bit-equal cost: the lower epsilon-arc index wins, so the
-    // backpointer does not depend on thread scheduling (the reference keeps whichever came
-    // first in its LIFO order, faster-decoder.cc:107-112; an incumbent from the emitting
-    // phase stays on a tie in both).
-    tie_only = cur_is_eps && mine.cost == cur.cost && mine.arg < cur.arg;
-    // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
-    const bool replace = mine.cost < cur.cost || tie_only ||
-                         (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
-    if (!replace) return;
-    HVal got = cas_hval(&B.table[h].val, cur, mine);
-    if (got.cost == cur.cost && got.arg == cur.arg) break;
-    cur = got;
+  bool owner;
+  HVal cur;
+  const uint32_t h = table_arrive(P, B, sh, epoch, state, mine, nullptr, nullptr, &owner, &cur);
+  if (h == kNoIdx) return;
+  if (!owner) {
+    bool tie_only;
+    while (true) {
+      const bool cur_is_eps = (cur.arg >> 63) != 0;
+      // Two epsilon arrivals with bit-equal cost: the lower epsilon-arc index wins, so the
+      // backpointer does not depend on thread scheduling (the reference keeps whichever came
+      // first in its LIFO order, faster-decoder.cc:107-112; an incumbent from the emitting
+      // phase stays on a tie in both).
+      tie_only = cur_is_eps && mine.cost == cur.cost && mine.arg < cur.arg;
+      // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
+      const bool replace = mine.cost < cur.cost || tie_only ||
+                           (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
+      if (!replace) return;
+      HVal got = cas_hval(&B.table[h].val, cur, mine);
+      if (got.cost == cur.cost && got.arg == cur.arg) break;
+      cur = got;
+    }
+    if (tie_only) return;  // same cost: nothing new to expand
   }
-  if (tie_only) return;  // same cost: nothing new to expand
   if (dst_word & kEpsFlag) {
     const uint32_t pos = atomicAdd(q_next_n, 1u);
     if (pos < P.qcap) {
@@ -738,8 +777,9 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
 // (faster-decoder.cc:71-117).
 template <bool SIMPLE>
 __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Shared &sh,
-                                           uint2 entry, unsigned long long cstar_key,
-                                           double cstar, uint2 *q_next, uint32_t *q_next_n,
+                                           uint32_t epoch, uint2 entry,
+                                           unsigned long long cstar_key, double cstar,
+                                           uint2 *q_next, uint32_t *q_next_n,
                                            uint32_t *eps_count) {
   const uint32_t slot = entry.x;
   // the worklist entry names the state: its record is requested together with the token
@@ -747,14 +787,14 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
 #if KD_OPT_QSTATE
   const int4 st = gld(P.st + 2 * static_cast<size_t>(entry.y));
 #endif
-  const HVal v = ld_hval(&B.table[slot].val);
-  // {state, number}: same sector as the value, requested together with it
-  const int2 ki = ld_key_idx(&B.table[slot].key);
+  // value, state and number of the token: one sector, one 256-bit load
+  const EntryWords w = ld_entry(B.table + slot);
+  const HVal v = w.val;
   const bool is_eps = (v.arg >> 63) != 0;
   // a token iff cost < C*, or it came from an epsilon arc (then cost <= C*)
-  if (v.cost == kEmptyCost || !(SIMPLE || v.cost < cstar_key || is_eps)) return;
+  if (!(SIMPLE || v.cost < cstar_key || is_eps)) return;
 #if !KD_OPT_QSTATE
-  const int4 st = gld(P.st + 2 * static_cast<size_t>(ki.x));
+  const int4 st = gld(P.st + 2 * static_cast<size_t>(w.key));
 #endif
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
@@ -763,8 +803,8 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
     const int4 arc = gld(P.n_arc + a);
     const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
-    eps_arrival<SIMPLE>(P, B, sh, static_cast<uint32_t>(arc.z), dkey(nc), static_cast<uint32_t>(a),
-                static_cast<uint32_t>(ki.y), cstar_key, q_next, q_next_n);
+    eps_arrival<SIMPLE>(P, B, sh, epoch, static_cast<uint32_t>(arc.z), dkey(nc),
+                        static_cast<uint32_t>(a), w.idx, cstar_key, q_next, q_next_n);
   }
 }
 
@@ -921,7 +961,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     __syncthreads();
     uint2 *qc = cur ? q1 : q0, *qx = cur ? q0 : q1;
     for (uint32_t p = tid; p < qn; p += THREADS)
-      expand_eps<SIMPLE>(P, B, sh, qc[p], cstar_key, cstar, qx, &sh.q_n[cur ^ 1], &eps_count);
+      expand_eps<SIMPLE>(P, B, sh, ls.epoch, qc[p], cstar_key, cstar, qx, &sh.q_n[cur ^ 1], &eps_count);
     __syncthreads();
     cur ^= 1;
     ++sweeps;
@@ -964,8 +1004,9 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       v[u].arg = kEmptyArg;
       key[u] = kEmptyKey;
       if (h[u] != kNoIdx) {
-        v[u] = ld_hval(&B.table[h[u]].val);
-        key[u] = ld_key(&B.table[h[u]].key);
+        const EntryWords w = ld_entry(B.table + h[u]);
+        v[u] = w.val;
+        key[u] = w.key;
       }
     }
     // the tokens close to the best also go to the front list (warp-aggregated append)
@@ -1015,7 +1056,9 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
           my_state = key[u];
         }
       }
-      st_wipe(&B.table[h[u]]);
+      // the entry is free again (its contents stay: the next owner overwrites them).  Every
+      // entry in use is released by this pass, so the whole word can go: a plain store
+      B.bitmap[h[u] >> 5] = 0u;
     }
   }
   double bmin;
@@ -1049,6 +1092,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.best_idx = -1;
       ls.best_state = -1;
     }
+    ls.epoch = ls.epoch + 1u == 0xFFFFFFFFu ? 0u : ls.epoch + 1u;  // (0xFFFFFFFF: never-written entries)
     ls.st_sweeps += sweeps;
     ls.st_claimed += m;
     ls.st_eps_arcs += sh.acc_eps;
@@ -1060,40 +1104,25 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   __syncthreads();
 }
 
-// Recombines one emitting arc that survived pruning at its destination state.
-// The key and the value of the first probed slot are loaded together (same
-// 32-byte sector): the usual case -- the state already has its slot -- then costs
-// one round trip before the 128-bit CAS instead of two.
-__device__ __forceinline__ void insert_probed(const Params &P, const LaneBuf &B, Shared &sh,
-                                              uint32_t a, unsigned long long nk, uint32_t tok_abs,
-                                              int2 no, int32_t k0, HVal cur) {
-  // `no` = e_no[a]; (k0, cur) = (key, value) read from the first probed slot of its state
-  const int32_t state = no.x & 0x7FFFFFFF;
+// Recombines one emitting arc that survived pruning at its destination state: the entry
+// keeps the lexicographic minimum of (cost, arc index).
+__device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
+                                           uint32_t epoch, uint32_t a, unsigned long long nk,
+                                           uint32_t tok_abs) {
+  const int2 no = gld(P.e_no + a);
   HVal mine;
   mine.cost = nk;
   mine.arg = (static_cast<unsigned long long>(a) << 32) | tok_abs;
-  const uint32_t h0 = table_hash(P, state);
-  uint32_t h = h0;
-  if (k0 != state) {
-    h = table_slot_from(P, B, sh, state, h0, k0, no.x < 0 ? B.queue : nullptr, &sh.q_n[0]);
-    if (h == kNoIdx) return;
-    // a freshly claimed slot holds the empty value; a slot found further along is re-read
-    if (h != h0 || k0 != kEmptyKey) cur = ld_hval(&B.table[h].val);
-  }
+  bool owner;
+  HVal cur;
+  const uint32_t h = table_arrive(P, B, sh, epoch, no.x & 0x7FFFFFFF, mine,
+                                  no.x < 0 ? B.queue : nullptr, &sh.q_n[0], &owner, &cur);
+  if (h == kNoIdx || owner) return;
   while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
     HVal got = cas_hval(&B.table[h].val, cur, mine);
     if (got.cost == cur.cost && got.arg == cur.arg) return;
     cur = got;
   }
-}
-
-__device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Shared &sh,
-                                           uint32_t a, unsigned long long nk, uint32_t tok_abs) {
-  const int2 no = gld(P.e_no + a);
-  const uint32_t h0 = table_hash(P, no.x & 0x7FFFFFFF);
-  const int32_t k0 = ld_key(&B.table[h0].key);
-  const HVal cur = ld_hval(&B.table[h0].val);  // same sector as the key: one round trip for both
-  insert_probed(P, B, sh, a, nk, tok_abs, no, k0, cur);
 }
 
 
@@ -1518,7 +1547,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
             } else if (SIMPLE) {
               atomicOr(&sh.status, kStatusCandOverflow);
             } else {
-              insert_arc(P, B, sh, aa[u], nk, tok_abs);  // buffer full: recombine now
+              insert_arc(P, B, sh, ls.epoch, aa[u], nk, tok_abs);  // buffer full: recombine now
             }
             if (nw < my_min) {
               my_min = nw;
@@ -1566,7 +1595,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
       min_stored = fmin(min_stored, stored);
       nk = dkey(stored);
     }
-    insert_arc(P, B, sh, c.z, nk, c.w);
+    insert_arc(P, B, sh, ls.epoch, c.z, nk, c.w);
   }
   double closure_cutoff = cstar;
   if (SIMPLE) {
@@ -1610,21 +1639,25 @@ constexpr int advance_max_regs(int threads, int min_blocks) {
 
 // The start token (faster-decoder.cc:46-52): cost 0 at Start(), no arc, no predecessor.
 // One thread; the caller closes it over the epsilon arcs and commits.
-__device__ __forceinline__ void lane_start_token(const Params &P, const LaneBuf &B, Shared &sh) {
+__device__ __forceinline__ void lane_start_token(const Params &P, const LaneBuf &B, Shared &sh,
+                                                 uint32_t epoch) {
   const int4 st = gld(P.st + 2 * static_cast<size_t>(P.start));
-  const uint32_t h = table_slot(P, B, sh, P.start, st.w > 0 ? B.queue : nullptr, &sh.q_n[0]);
-  if (h == kNoIdx) return;
   HVal v;
   v.cost = dkey(0.0);
   v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
-  *reinterpret_cast<ulonglong2 *>(&B.table[h].val) = make_ulonglong2(v.cost, v.arg);
+  bool owner;
+  HVal unused;
+  table_arrive(P, B, sh, epoch, P.start, v, st.w > 0 ? B.queue : nullptr, &sh.q_n[0], &owner,
+               &unused);
 }
 
 __device__ __forceinline__ void lane_state_reset(LaneState &ls) {
   // (word by word, in place: a local copy of the struct would live on the stack)
+  const uint32_t epoch = ls.epoch;  // entries written before this InitDecoding must stay stale
   uint32_t *w = reinterpret_cast<uint32_t *>(&ls);
 #pragma unroll 1
   for (int i = 0; i < static_cast<int>(sizeof(LaneState) / 4); ++i) w[i] = 0u;
+  ls.epoch = epoch;
   ls.best_cost = __longlong_as_double(0x7FF0000000000000ll);
   ls.best_idx = -1;
   ls.best_state = -1;
@@ -1870,11 +1903,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
     if (tid == 0) {
       sB = lane_buffers(P, it.lane);
       sB.s_list = s_list;
-      if (init_pass) {
-        lane_state_reset(ls);
-      } else {
-        ls = P.lanes[it.lane];
-      }
+      ls = P.lanes[it.lane];
+      if (init_pass) lane_state_reset(ls);
       sh.status = ls.status;
       sh.list_n = 0;
       sh.q_n[0] = 0;
@@ -1886,7 +1916,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
       double cstar, good_cut, mid_cut;
       int n_in = 0, frame = 0;
       if (init_pass) {
-        if (tid == 0) lane_start_token(P, B, sh);
+        if (tid == 0) lane_start_token(P, B, sh, ls.epoch);
         cstar = SIMPLE ? static_cast<double>(P.beam) : 3.4028234663852886e+38 /* FLT_MAX */;
         good_cut = mid_cut = 0.0;
         __syncthreads();
@@ -1981,13 +2011,14 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
   LaneBuf B = lane_buffers(P, lane);
   B.s_list = s_list;
   if (tid == 0) {
+    ls = P.lanes[lane];
     lane_state_reset(ls);
     sh.status = 0;
     sh.list_n = 0;
     sh.q_n[0] = 0;
   }
   __syncthreads();
-  if (tid == 0) lane_start_token(P, B, sh);
+  if (tid == 0) lane_start_token(P, B, sh, ls.epoch);
   __syncthreads();
   if (P.simple) {
     // SimpleDecoder::InitDecoding: closure under cutoff 0 + beam (simple-decoder.cc:29-41,196-204)

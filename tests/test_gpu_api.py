@@ -443,16 +443,19 @@ def test_single_utterance_decoders_run_concurrently_from_python_threads():
     opts = kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"], min_active=o["min_active"])
     n_threads = 4
     errors = []
+    # (the .npz reader is not thread-safe: everything is read before the threads start)
+    logps = [gc.logp(u) for u in range(gc.n_utts)]
+    wants = [(gc.best(u, True), gc.reached_final(u)) for u in range(gc.n_utts)]
 
     def work(k):
         try:
             dec = kd.FasterDecoder(graph, opts)
             for rep in range(6):
                 u = (k + rep) % gc.n_utts
-                dec.decode(kd.DecodableCtc(gc.logp(u)))
+                dec.decode(kd.DecodableCtc(logps[u]))
                 ok, best = dec.get_best_path()
-                want = gc.best(u, True)
-                assert ok == want.ok and dec.reached_final() == gc.reached_final(u)
+                want, rf = wants[u]
+                assert ok == want.ok and dec.reached_final() == rf
                 assert kd.get_linear_symbol_sequence(best)[2] == [int(x) for x in want.osyms]
         except Exception as e:  # noqa: BLE001
             errors.append((k, repr(e)))
