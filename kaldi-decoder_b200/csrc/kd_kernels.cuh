@@ -54,6 +54,9 @@
 #ifndef KD_OPT_CAND_CACHED
 #define KD_OPT_CAND_CACHED 0  // candidate buffer / front list with default (write-back) caching instead of streaming
 #endif
+#ifndef KD_SINGLE_PASS_TILES
+#define KD_SINGLE_PASS_TILES 1   // blocks of at most this many scan tiles take one pass
+#endif
 #ifndef KD_OPT_SLIST
 #define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
 #endif
@@ -1334,7 +1337,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   static_assert(TT <= kFrontCap, "front list smaller than a scan tile");
   // (a block that fits one tile is scanned in one pass: the second pass would cost three
   // more dependent round trips and has little left to tighten)
-  const bool single_pass = KD_OPT_SINGLE_PASS && ls.n_tok <= TT;
+  const bool single_pass = KD_OPT_SINGLE_PASS && ls.n_tok <= KD_SINGLE_PASS_TILES * TT;
   for (int pass = single_pass ? 1 : 0; pass < 2; ++pass) {
     // pass 0 reads the front list the commit wrote, unless it overflowed (then it filters the block)
     const bool front_list =
