@@ -432,6 +432,7 @@ struct Shared {
   int status;
   int item;
   int32_t rows_ready;
+  int load_first;          // table arrivals read the entry before they try to claim it (see table_arrive)
   int any_final;           // best-path selection scratch
   uint32_t best_tok;
   int row_pending;         // a bulk copy of the next frame's row is in flight
@@ -582,6 +583,17 @@ __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf 
                                                  uint2 *eps_queue, uint32_t *eps_queue_n,
                                                  bool *owner, HVal *cur) {
   uint32_t h = table_hash(P, state);
+  // Frames in which most arrivals meet a state that is already there (H-like graphs: every
+  // state is reached through hundreds of arcs) look at the entry first: a valid entry of
+  // this state saves the atomic.  The bitmap stays the authority for everything else.
+  if (sh.load_first != 0) {
+    const EntryWords w = ld_entry(B.table + h);
+    if (w.epoch == epoch && w.key == state) {
+      *owner = false;
+      *cur = w.val;
+      return h;
+    }
+  }
   for (uint32_t probe = 0; probe < P.hcap; ++probe) {
     const uint32_t bit = 1u << (h & 31u);
     const uint32_t old = atomicOr(B.bitmap + (h >> 5), bit);
@@ -1096,6 +1108,8 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
       ls.best_state = -1;
     }
     ls.epoch = ls.epoch + 1u == 0xFFFFFFFFu ? 0u : ls.epoch + 1u;  // (0xFFFFFFFF: never-written entries)
+    // the next frame resembles this one: more than two arrivals per state -> entry first
+    sh.load_first = sh.cand_n > 2u * m ? 1 : 0;
     ls.st_sweeps += sweeps;
     ls.st_claimed += m;
     ls.st_eps_arcs += sh.acc_eps;
@@ -1913,6 +1927,8 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
       sh.q_n[0] = 0;
       sh.rows_ready = P.progress != nullptr ? 0 : 0x7FFFFFFF;
       sh.yield = 0;
+      sh.load_first = 0;
+      sh.cand_n = 0;
     }
     __syncthreads();
     while (true) {
@@ -2019,6 +2035,8 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     sh.status = 0;
     sh.list_n = 0;
     sh.q_n[0] = 0;
+    sh.load_first = 0;
+    sh.cand_n = 0;
   }
   __syncthreads();
   if (tid == 0) lane_start_token(P, B, sh, ls.epoch);
