@@ -57,6 +57,12 @@
 #ifndef KD_SINGLE_PASS_TILES
 #define KD_SINGLE_PASS_TILES 1   // blocks of at most this many scan tiles take one pass
 #endif
+#ifndef KD_OPT_PREFETCH_NO
+#define KD_OPT_PREFETCH_NO 0  // L2 prefetch of a candidate's (nextstate, olabel) record when it is appended
+#endif
+#ifndef KD_OPT_DEFER
+#define KD_OPT_DEFER 1         // arrivals at states already in the table are recombined in a second pass
+#endif
 #ifndef KD_OPT_SLIST
 #define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
 #endif
@@ -432,6 +438,7 @@ struct Shared {
   int status;
   int item;
   int32_t rows_ready;
+  uint32_t park_n;         // arrivals parked for the second recombination pass
   int load_first;          // table arrivals read the entry before they try to claim it (see table_arrive)
   int any_final;           // best-path selection scratch
   uint32_t best_tok;
@@ -581,12 +588,13 @@ __device__ __forceinline__ uint32_t register_claim(const Params &P, const LaneBu
 __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf &B, Shared &sh,
                                                  uint32_t epoch, int32_t state, HVal mine,
                                                  uint2 *eps_queue, uint32_t *eps_queue_n,
-                                                 bool *owner, HVal *cur) {
-  uint32_t h = table_hash(P, state);
+                                                 bool *owner, HVal *cur,
+                                                 uint32_t h_start = kNoIdx) {
+  uint32_t h = h_start == kNoIdx ? table_hash(P, state) : h_start;
   // Frames in which most arrivals meet a state that is already there (H-like graphs: every
   // state is reached through hundreds of arcs) look at the entry first: a valid entry of
   // this state saves the atomic.  The bitmap stays the authority for everything else.
-  if (sh.load_first != 0) {
+  if (sh.load_first != 0 && h_start == kNoIdx) {
     const EntryWords w = ld_entry(B.table + h);
     if (w.epoch == epoch && w.key == state) {
       *owner = false;
@@ -1228,6 +1236,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     sh.cut_fkey = fkey(__int_as_float(0x7F800000));
     sh.acc_emit = sh.acc_expanded = sh.acc_items = 0;
     sh.cand_n = 0;
+    sh.park_n = 0;
   }
   double wc;
   float abf;
@@ -1550,6 +1559,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
           if (lane == 0) cbase = atomicAdd(&sh.cand_n, __popc(cmask));
           cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
           if (is_cand) {
+#if KD_OPT_PREFETCH_NO
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P.e_no + aa[u]));
+#endif
             const uint32_t tok_abs = base + t_tok[tt[u]];
             const unsigned long long nk = dkey(nw);
             const uint32_t e = cbase + __popc(cmask & ((1u << lane) - 1u));
@@ -1599,6 +1611,86 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // loads together -- the recombination gets faster, the other phases of the co-resident
   // lanes slower by as much; claiming the slot with the CAS before any probe load.)
   double min_stored = inf;  // SIMPLE only
+#if KD_OPT_DEFER
+  // Two passes.  Pass A: every arrival tries to claim its state's entry; the ones that do
+  // (80 %) write it and are done.  An arrival that finds the entry in use is parked in
+  // shared memory (the scan's tile arrays are idle now) instead of being recombined on the
+  // spot: within a warp the two cases would run one after the other, and every step of the
+  // warp would pay the entry load and the CAS of its few latecomers.  Pass B recombines the
+  // parked arrivals, all threads on the same path; the barrier in between also means that
+  // every entry they look at has been written.
+  uint4 *parked = reinterpret_cast<uint4 *>(t_cost);
+  constexpr uint32_t kParkCap = (24u * TT) / 16u;
+  const bool defer = !SIMPLE && sh.load_first == 0;
+  for (uint32_t e = tid; e < n_cand; e += THREADS) {
+    const uint4 c = KD_OPT_CAND_CACHED ? __ldcg(B.cand + e) : __ldcs(B.cand + e);
+    unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
+    if (!(nk < cstar_key)) continue;  // faster-decoder.cc:211 / simple-decoder.cc:170, final cutoff
+    if (SIMPLE) {
+      // SimpleDecoder prunes on (cost + w) + ac but stores cost + float(w + ac)
+      // (simple-decoder.cc:168 vs simple-decoder.h:96)
+      const int2 iw = gld(P.e_iw + c.z);
+      const float ac = -(ROW_SMEM ? s_row[iw.x - 1] : __ldcg(row_g + iw.x - 1));
+      const double stored = B.a_cost[c.w] + static_cast<double>(__fadd_rn(__int_as_float(iw.y), ac));
+      min_stored = fmin(min_stored, stored);
+      nk = dkey(stored);
+    }
+    if (!defer) {
+      insert_arc(P, B, sh, ls.epoch, c.z, nk, c.w);
+      continue;
+    }
+    const int2 no = gld(P.e_no + c.z);
+    const int32_t state = no.x & 0x7FFFFFFF;
+    const uint32_t h = table_hash(P, state);
+    const uint32_t bit = 1u << (h & 31u);
+    const uint32_t old = atomicOr(B.bitmap + (h >> 5), bit);
+    if ((old & bit) == 0) {
+      HVal mine;
+      mine.cost = nk;
+      mine.arg = (static_cast<unsigned long long>(c.z) << 32) | c.w;
+      const uint32_t pos =
+          register_claim(P, B, sh, h, state, no.x < 0 ? B.queue : nullptr, &sh.q_n[0]);
+      st_entry(B.table + h, mine, state, pos, ls.epoch);
+    } else {
+      const uint32_t slot = atomicAdd(&sh.park_n, 1u);
+      if (slot < kParkCap) {
+        parked[slot] = make_uint4(h, static_cast<uint32_t>(no.x), e, 0u);
+      } else {
+        insert_arc(P, B, sh, ls.epoch, c.z, nk, c.w);  // no room: on the spot
+      }
+    }
+  }
+  __syncthreads();
+  if (defer) {
+    const uint32_t n_park = min(sh.park_n, kParkCap);
+    for (uint32_t i = tid; i < n_park; i += THREADS) {
+      const uint4 r = parked[i];
+      // the arrival and the entry it met: two independent loads, one round trip
+      const uint4 c = KD_OPT_CAND_CACHED ? __ldcg(B.cand + r.z) : __ldcs(B.cand + r.z);
+      const EntryWords w = ld_entry(B.table + r.x);
+      const int32_t state = static_cast<int32_t>(r.y & 0x7FFFFFFFu);
+      HVal mine;
+      mine.cost = (static_cast<unsigned long long>(c.y) << 32) | c.x;
+      mine.arg = (static_cast<unsigned long long>(c.z) << 32) | c.w;
+      uint32_t h = r.x;
+      HVal cur = w.val;
+      if (w.key != state || w.epoch != ls.epoch) {
+        // the entry belongs to another state (or, parked by the overflow path of another
+        // thread, is still on its way): the regular walk, from this entry on
+        bool owner;
+        h = table_arrive(P, B, sh, ls.epoch, state, mine,
+                         static_cast<int32_t>(r.y) < 0 ? B.queue : nullptr, &sh.q_n[0], &owner,
+                         &cur, w.key != state && w.epoch == ls.epoch ? ((r.x + 1) & P.hmask) : r.x);
+        if (h == kNoIdx || owner) continue;
+      }
+      while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
+        HVal got = cas_hval(&B.table[h].val, cur, mine);
+        if (got.cost == cur.cost && got.arg == cur.arg) break;
+        cur = got;
+      }
+    }
+  }
+#else
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
     const uint4 c = KD_OPT_CAND_CACHED ? __ldcg(B.cand + e) : __ldcs(B.cand + e);
     unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
@@ -1614,6 +1706,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     }
     insert_arc(P, B, sh, ls.epoch, c.z, nk, c.w);
   }
+#endif
   double closure_cutoff = cstar;
   if (SIMPLE) {
     // ProcessNonemitting's cutoff: best stored cost + beam (simple-decoder.cc:196-204)
