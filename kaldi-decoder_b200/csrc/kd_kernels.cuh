@@ -86,6 +86,7 @@ constexpr int32_t kEmptyKey = -1;
 constexpr unsigned long long kEmptyCost = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned long long kEmptyArg = 0xFFFFFFFFFFFFFFFFull;
 constexpr uint32_t kNoIdx = 0xFFFFFFFFu;
+constexpr uint32_t kRetry = 0xFFFFFFFEu;  // table_arrive: the entry is claimed but not written yet
 constexpr int kLabelTableMinDegree = 16;  // states with at least this many emitting arcs get a label table
 constexpr int kOrderBins = 512;           // buckets of the per-frame label order (1/16 wide)
 constexpr int kMaxOrderCols = 2048;       // widest log-prob row for which the label order is built
@@ -578,17 +579,25 @@ __device__ __forceinline__ uint32_t register_claim(const Params &P, const LaneBu
   return pos;
 }
 
-// The arrival `mine` at `state`.  Returns the state's slot, or kNoIdx on overflow.
+// The arrival `mine` at `state`.  Returns the state's slot, kNoIdx on overflow, or kRetry.
 //   *owner = true : the state was not in the table; this thread took an entry for it and has
 //                   written it, value included -- nothing else to do;
 //   *owner = false: the state has an entry; *cur is its value as just read (the caller
 //                   recombines with a CAS on Entry::val).
 // Probing is linear over the bitmap: the first entry of the probe sequence whose bit this
 // thread flips is its own; an entry whose bit was already set belongs to the state it names.
+// An entry can be claimed (bit set) and not written yet: its owner is between the atomicOr
+// and the store.  With `may_wait` false such an entry makes the call return kRetry and the
+// caller comes back after a barrier (the epsilon closure: the source token is expanded again
+// in the next sweep).  With `may_wait` true the thread re-reads until the store has landed --
+// nanoseconds; if the owner is a thread of the same warp on the other side of the divergent
+// branch this relies on independent thread scheduling (sm_70+) to let it run, and the wait is
+// bounded: it ends in a loud table-overflow status, never in a hang.  The two-pass
+// recombination below keeps the bulk of the arrivals away from this case.
 __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf &B, Shared &sh,
                                                  uint32_t epoch, int32_t state, HVal mine,
                                                  uint2 *eps_queue, uint32_t *eps_queue_n,
-                                                 bool *owner, HVal *cur,
+                                                 bool may_wait, bool *owner, HVal *cur,
                                                  uint32_t h_start = kNoIdx) {
   uint32_t h = h_start == kNoIdx ? table_hash(P, state) : h_start;
   // Frames in which most arrivals meet a state that is already there (H-like graphs: every
@@ -613,12 +622,16 @@ __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf 
     }
     // in use: by whom?  (its owner's store may still be on its way: the epoch tells)
     EntryWords w = ld_entry(B.table + h);
-    for (uint32_t spins = 0; w.epoch != epoch; ++spins) {
-      if (spins > (1u << 22)) {  // never in a correct run: fail instead of hanging
-        atomicOr(&sh.status, kStatusHashOverflow);
-        return kNoIdx;
+    if (w.epoch != epoch) {
+      if (!may_wait) return kRetry;
+      for (uint32_t spins = 0; w.epoch != epoch; ++spins) {
+        if (spins > (1u << 22)) {  // never in a correct run: fail instead of hanging
+          atomicOr(&sh.status, kStatusHashOverflow);
+          return kNoIdx;
+        }
+        __nanosleep(64);
+        w = ld_entry(B.table + h);
       }
-      w = ld_entry(B.table + h);
     }
     if (w.key == state) {
       *owner = false;
@@ -754,19 +767,23 @@ __device__ void lane_cutoff(const Params &P, const double *cost, int n, const La
 // A token that was created or improved is queued for expansion when its state
 // has epsilon arcs (flag in the arc's nextstate word).
 template <bool SIMPLE>
-__device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
+__device__ __forceinline__ bool eps_arrival(const Params &P, const LaneBuf &B, Shared &sh,
                                             uint32_t epoch, uint32_t dst_word,
                                             unsigned long long cost_key, uint32_t arc,
                                             uint32_t src_number, unsigned long long cstar_key,
                                             uint2 *q_next, uint32_t *q_next_n) {
+  // (returns false if the destination's entry is claimed but not written yet: the caller
+  // expands the source token again in the next sweep)
   const int32_t state = static_cast<int32_t>(dst_word & ~kEpsFlag);
   HVal mine;
   mine.cost = cost_key;
   mine.arg = (static_cast<unsigned long long>(arc | kEpsFlag) << 32) | src_number;
   bool owner;
   HVal cur;
-  const uint32_t h = table_arrive(P, B, sh, epoch, state, mine, nullptr, nullptr, &owner, &cur);
-  if (h == kNoIdx) return;
+  const uint32_t h =
+      table_arrive(P, B, sh, epoch, state, mine, nullptr, nullptr, false, &owner, &cur);
+  if (h == kRetry) return false;
+  if (h == kNoIdx) return true;
   if (!owner) {
     bool tie_only;
     while (true) {
@@ -779,12 +796,12 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
       // (SimpleDecoder search: every table entry is a token, simple-decoder.cc:224-231)
       const bool replace = mine.cost < cur.cost || tie_only ||
                            (!SIMPLE && !cur_is_eps && !(cur.cost < cstar_key));
-      if (!replace) return;
+      if (!replace) return true;
       HVal got = cas_hval(&B.table[h].val, cur, mine);
       if (got.cost == cur.cost && got.arg == cur.arg) break;
       cur = got;
     }
-    if (tie_only) return;  // same cost: nothing new to expand
+    if (tie_only) return true;  // same cost: nothing new to expand
   }
   if (dst_word & kEpsFlag) {
     const uint32_t pos = atomicAdd(q_next_n, 1u);
@@ -794,6 +811,7 @@ __device__ __forceinline__ void eps_arrival(const Params &P, const LaneBuf &B, S
       atomicOr(&sh.status, kStatusQueueOverflow);
     }
   }
+  return true;
 }
 
 // Expands the epsilon arcs of the token in table slot `slot`
@@ -822,12 +840,24 @@ __device__ __forceinline__ void expand_eps(const Params &P, const LaneBuf &B, Sh
   if (st.w == 0) return;
   const double cost = dunkey(v.cost);
   *eps_count += static_cast<uint32_t>(st.w);
+  bool again = false;
   for (int a = st.z; a < st.z + st.w; ++a) {
     const int4 arc = gld(P.n_arc + a);
     const double nc = cost + widen(__int_as_float(arc.y));
     if (nc > cstar) continue;  // faster-decoder.cc:92
-    eps_arrival<SIMPLE>(P, B, sh, epoch, static_cast<uint32_t>(arc.z), dkey(nc),
-                        static_cast<uint32_t>(a), w.idx, cstar_key, q_next, q_next_n);
+    if (!eps_arrival<SIMPLE>(P, B, sh, epoch, static_cast<uint32_t>(arc.z), dkey(nc),
+                             static_cast<uint32_t>(a), w.idx, cstar_key, q_next, q_next_n))
+      again = true;
+  }
+  if (again) {
+    // some destination was being written by another thread: this token is expanded again in
+    // the next sweep (arrivals that already went through repeat with equal cost: no effect)
+    const uint32_t pos = atomicAdd(q_next_n, 1u);
+    if (pos < P.qcap) {
+      q_next[pos] = entry;
+    } else {
+      atomicOr(&sh.status, kStatusQueueOverflow);
+    }
   }
 }
 
@@ -1141,7 +1171,7 @@ __device__ __forceinline__ void insert_arc(const Params &P, const LaneBuf &B, Sh
   bool owner;
   HVal cur;
   const uint32_t h = table_arrive(P, B, sh, epoch, no.x & 0x7FFFFFFF, mine,
-                                  no.x < 0 ? B.queue : nullptr, &sh.q_n[0], &owner, &cur);
+                                  no.x < 0 ? B.queue : nullptr, &sh.q_n[0], true, &owner, &cur);
   if (h == kNoIdx || owner) return;
   while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
     HVal got = cas_hval(&B.table[h].val, cur, mine);
@@ -1679,8 +1709,9 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         // thread, is still on its way): the regular walk, from this entry on
         bool owner;
         h = table_arrive(P, B, sh, ls.epoch, state, mine,
-                         static_cast<int32_t>(r.y) < 0 ? B.queue : nullptr, &sh.q_n[0], &owner,
-                         &cur, w.key != state && w.epoch == ls.epoch ? ((r.x + 1) & P.hmask) : r.x);
+                         static_cast<int32_t>(r.y) < 0 ? B.queue : nullptr, &sh.q_n[0], true,
+                         &owner, &cur,
+                         w.key != state && w.epoch == ls.epoch ? ((r.x + 1) & P.hmask) : r.x);
         if (h == kNoIdx || owner) continue;
       }
       while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
@@ -1757,7 +1788,7 @@ __device__ __forceinline__ void lane_start_token(const Params &P, const LaneBuf 
   v.arg = (static_cast<unsigned long long>(kNoArc) << 32) | kNoPrev;
   bool owner;
   HVal unused;
-  table_arrive(P, B, sh, epoch, P.start, v, st.w > 0 ? B.queue : nullptr, &sh.q_n[0], &owner,
+  table_arrive(P, B, sh, epoch, P.start, v, st.w > 0 ? B.queue : nullptr, &sh.q_n[0], true, &owner,
                &unused);
 }
 
