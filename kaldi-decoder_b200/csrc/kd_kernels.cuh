@@ -100,7 +100,10 @@ constexpr int kWin = KD_WIN;
 #define KD_TILE_TOKENS 2
 #endif
 constexpr int kTileTokens = KD_TILE_TOKENS;  // tokens per thread in one scan tile
-constexpr int kListSmem = KD_OPT_SLIST ? 1024 : 0;  // slot-list entries kept in shared memory
+#ifndef KD_LIST_SMEM
+#define KD_LIST_SMEM 1024
+#endif
+constexpr int kListSmem = KD_OPT_SLIST ? KD_LIST_SMEM : 0;  // slot-list entries kept in shared memory
 constexpr int kFrontCap = 2048;           // records of the per-lane front list (>= the largest scan tile)
 constexpr uint32_t kLookupFlag = 0x80000000u;  // in t_beg: expand this token by label lookup  // commit numbering: token goes behind the "good" ones
 
