@@ -129,3 +129,26 @@ def parity_table(g, mats, opts, gpu_paths, threads=None):
         else:
             cls["real"] += 1
     return out
+
+
+def build_cpp_drop_in(out_dir):
+    """Compiles tests/cpp/drop_in.cc -- a caller written against the reference's include paths
+    -- with the B200 sources and links it against libkd_b200.so.  Returns the binary's path."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = shutil.which("g++")
+    if cxx is None:
+        return None
+    pkg = os.path.join(root, "kaldi-decoder_b200")
+    out = os.path.join(str(out_dir), "drop_in")
+    cmd = [cxx, "-std=c++17", "-O1", "-I", os.path.join(pkg, "compat"), "-I", root,
+           "-I", os.path.join(pkg, "csrc", "minifst"), "-I", os.path.join(root, "include"),
+           os.path.join(root, "tests", "cpp", "drop_in.cc"),
+           os.path.join(pkg, "csrc", "faster-decoder.cc"), os.path.join(pkg, "csrc", "decodable-ctc.cc"),
+           os.path.join(pkg, "csrc", "fst-io.cc"), "-L", os.path.join(pkg, "lib"), "-lkd_b200",
+           "-Wl,-rpath," + os.path.join(pkg, "lib"), "-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out

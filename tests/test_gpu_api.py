@@ -466,3 +466,37 @@ def test_single_utterance_decoders_run_concurrently_from_python_threads():
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_cpp_caller_written_against_the_reference_headers_runs(tmp_path):
+    """The C++ drop-in caller (tests/cpp/drop_in.cc: the reference's include paths, Decode /
+    InitDecoding + AdvanceDecoding / GetBestPath / ReachedFinal / NumFramesDecoded) against
+    the reference's results frozen in the golden fixtures."""
+    import subprocess
+    import kaldi_decoder as kd
+    from common import build_cpp_drop_in
+    exe = build_cpp_drop_in(tmp_path)
+    if exe is None:
+        pytest.skip("no g++")
+    for name in ("hlg300_peaky", "hl300"):
+        gc = GoldenCase(name)
+        g = gc.graph
+        fst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                          g.weight, g.nextstate, g.final)
+        fst.write(str(tmp_path / "g.fst"))
+        lp = np.stack([gc.logp(u) for u in range(gc.n_utts)]).astype(np.float32)
+        lp.tofile(str(tmp_path / "lp.bin"))
+        o = gc.opts
+        r = subprocess.run([exe, str(tmp_path / "g.fst"), str(o["beam"]), str(o["max_active"]),
+                            str(o["min_active"]), str(tmp_path / "lp.bin"), str(gc.n_utts),
+                            str(gc.T), str(lp.shape[2])], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = r.stdout.strip().splitlines()
+        assert len(lines) == gc.n_utts
+        for u, ln in enumerate(lines):
+            f = ln.split()
+            want = gc.best(u, True)
+            assert int(f[0]) == u and int(f[1]) == int(want.ok), (name, ln)
+            assert int(f[2]) == int(gc.reached_final(u)) and int(f[3]) == gc.T, (name, ln)
+            assert [int(x) for x in f[5:]] == [int(x) for x in want.osyms], (name, u)
+            assert rel_close(float(f[4]), want.total_cost, 1e-4), (name, u, f[4], want.total_cost)

@@ -352,3 +352,30 @@ def test_dlpack_ingest_parses_the_capsule_and_rejects_host_arrays():
         with pytest.raises(ValueError, match="CUDA"):
             kd._from_dlpack(W(torch.zeros(3, 4)))
     gc.collect()
+
+
+def test_cpp_caller_written_against_the_reference_headers_builds(tmp_path):
+    """tests/cpp/drop_in.cc includes "kaldi-decoder/csrc/faster-decoder.h" and uses the
+    reference's C++ API (faster-decoder.h:65-107); it must compile and link against the B200
+    implementation, and -- without a GPU -- fail with the library's loud error, not a crash."""
+    import subprocess
+    from common import build_cpp_drop_in
+    exe = build_cpp_drop_in(tmp_path)
+    if exe is None:
+        pytest.skip("no g++")
+    gc = GoldenCase("h20_default")
+    g = gc.graph
+    import kaldi_decoder as kd
+    fst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                      g.weight, g.nextstate, g.final)
+    fst.write(str(tmp_path / "g.fst"))
+    lp = np.stack([gc.logp(u) for u in range(gc.n_utts)]).astype(np.float32)
+    lp.tofile(str(tmp_path / "lp.bin"))
+    o = gc.opts
+    r = subprocess.run([exe, str(tmp_path / "g.fst"), str(o["beam"]), str(o["max_active"]),
+                        str(o["min_active"]), str(tmp_path / "lp.bin"), str(gc.n_utts),
+                        str(gc.T), str(lp.shape[2])], capture_output=True, text=True, timeout=300)
+    if capi.device_count() == 0:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr[-500:])
+    else:
+        assert r.returncode == 0, r.stderr[-2000:]
