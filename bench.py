@@ -93,6 +93,10 @@ CONFIG_THREADS = {"C1": 160, "C2": 160, "C3": 0, "C4": 0}
 # tokens alive in one frame must stay below half of this (measured maxima: C1 500, C2 146k,
 # C3 49k, C4 142k tokens)
 CONFIG_HASH = {"C1": 1 << 14, "C2": 1 << 19, "C3": 1 << 18, "C4": 1 << 19}
+# backpointer-store records per lane (0 = library default: a share of the free memory).  The
+# store is garbage-collected when it fills up, which costs time: C2 and C4 keep ~1.6 M / ~1.1 M
+# records per utterance and get room for the whole utterance.
+CONFIG_ARENA = {"C1": 0, "C2": 2_200_000, "C3": 0, "C4": 1_800_000}
 CONFIG_NAME = {
     "C1": "H-500 CTC topology, 64 utts x T=1000 x V=500, beam 20, max_active 7000",
     "C2": "HL 200k-word lexicon trie, 256 utts x T=1000 x V=500, beam 20, max_active 7000",
@@ -300,7 +304,7 @@ def main():
     n_groups = args.groups if args.groups > 0 else CONFIG_GROUPS[args.config]
     dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=lanes * n_groups,
                            hash_capacity=args.hash_capacity or CONFIG_HASH[args.config],
-                           arena_records=args.arena_records,
+                           arena_records=args.arena_records or CONFIG_ARENA[args.config],
                            threads_per_lane=args.threads_per_lane or CONFIG_THREADS[args.config],
                            chunk_frames=args.chunk_frames)
     # every rank decodes its own utterances (seed differs per rank): weak scaling

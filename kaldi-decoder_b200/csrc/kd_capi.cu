@@ -638,7 +638,9 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   } else {
     size_t free_b = 0, total_b = 0;
     KD_CUDA_D(cudaMemGetInfo(&free_b, &total_b));
-    double budget = 0.5 * static_cast<double>(free_b) - static_cast<double>(table_bytes_per_lane * L);
+    // (0.7 of the free memory for tables + arena: the rest is left to the caller's matrices, the
+    // staging buffers of host input, and whatever else lives on the device)
+    double budget = 0.7 * static_cast<double>(free_b) - static_cast<double>(table_bytes_per_lane * L);
     long long per_lane = static_cast<long long>(budget / (20.0 * static_cast<double>(L)));
     d->arena_cap = std::max<long long>(1 << 16, std::min<long long>(per_lane, 1ll << 25));
   }
