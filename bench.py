@@ -392,7 +392,11 @@ def main():
     e2e = None
     if not args.no_e2e:
         dt_h, span_h, n_launch_h = timed(hptrs, capi.KD_MEM_HOST, args.steps, max(1, args.warmup))
+        st_h = dec.stats()
+        busy_h = sum(st_h[k] for k in ("cycles_cutoff", "cycles_expand", "cycles_closure", "cycles_commit"))
         e2e = {"value": frames_per_step / (dt_h / args.steps), "unit": UNIT,
+               # share of the lanes' time spent waiting for rows still on their way from the host
+               "input_wait_frac": st_h["cycles_input_wait"] / max(1, busy_h + st_h["cycles_input_wait"]),
                "h2d_bytes_per_step": int(lanes * T * V * 4), "d2h_bytes_per_step": d2h,
                "ms_per_step": dt_h / args.steps * 1e3,
                # what every rank's host link has to sustain; with several ranks uploading at

@@ -111,6 +111,9 @@ typedef struct kd_stats {
   int64_t cycles_scan;     /* part of cycles_expand before the exact cutoff       */
   int64_t arena_compactions; /* garbage collections of the backpointer arena (a lane's records
                               are compacted when a frame's tokens no longer fit)   */
+  int64_t cycles_input_wait; /* SM cycles lanes spent waiting for log-prob rows still on their
+                              way from the host (KD_MEM_HOST): the share of the search time
+                              that the upload, not the search, decides                */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

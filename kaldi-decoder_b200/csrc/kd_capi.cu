@@ -1676,6 +1676,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->arcs_evaluated += L.st_items;
     out->cycles_scan += L.cyc_scan;
     out->arena_compactions += L.st_compactions;
+    out->cycles_input_wait += L.cyc_wait;
   }
   return KD_OK;
 }

@@ -158,6 +158,7 @@ struct __align__(16) LaneState {
   long long cyc_cutoff, cyc_expand, cyc_closure, cyc_commit, cyc_scan;
   long long st_claimed;  // table slots claimed (tokens + arrivals later found >= C*)
   long long st_compactions;  // arena garbage collections
+  long long cyc_wait;        // SM cycles spent waiting for streamed log-prob rows (host input)
   uint32_t epoch;          // stamps the table entries of the current pass; survives InitDecoding
   uint32_t pad0;
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
@@ -2092,6 +2093,7 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
             }
             __threadfence();
             sh.rows_ready = ready;
+            ls.cyc_wait += clock64() - t0;
           }
           __syncthreads();
           if (sh.yield != 0) break;

@@ -43,7 +43,8 @@ class KdStats(C.Structure):
                                          "eps_arcs", "tokens_out", "max_tokens", "eps_sweeps",
                                          "cycles_cutoff", "cycles_expand", "cycles_closure",
                                          "cycles_commit", "slots_claimed", "candidates",
-                                         "arcs_evaluated", "cycles_scan", "arena_compactions")]
+                                         "arcs_evaluated", "cycles_scan", "arena_compactions",
+                                         "cycles_input_wait")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
