@@ -63,9 +63,6 @@
 #ifndef KD_OPT_DEFER
 #define KD_OPT_DEFER 1         // arrivals at states already in the table are recombined in a second pass
 #endif
-#ifndef KD_OPT_PAIRS
-#define KD_OPT_PAIRS 0          // recombination pass A takes two candidates per thread and step
-#endif
 #ifndef KD_OPT_SLIST
 #define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
 #endif
@@ -1659,58 +1656,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   uint4 *parked = reinterpret_cast<uint4 *>(t_cost);
   constexpr uint32_t kParkCap = (24u * TT) / 16u;
   const bool defer = !SIMPLE && sh.load_first == 0;
-#if KD_OPT_PAIRS
-  // (pass A, two candidates per thread and step: their loads and bitmap atomics overlap)
-  for (uint32_t e = tid; defer && e < n_cand; e += 2 * THREADS) {
-    uint4 c[2];
-    bool pass[2];
-    int2 no[2];
-    uint32_t old[2], h[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t ek = e + k * THREADS;
-      c[k] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
-      if (ek < n_cand) c[k] = KD_OPT_CAND_CACHED ? __ldcg(B.cand + ek) : __ldcs(B.cand + ek);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const unsigned long long nk = (static_cast<unsigned long long>(c[k].y) << 32) | c[k].x;
-      pass[k] = nk < cstar_key;  // faster-decoder.cc:211, final cutoff
-      no[k] = make_int2(0, 0);
-      if (pass[k]) no[k] = gld(P.e_no + c[k].z);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      h[k] = table_hash(P, no[k].x & 0x7FFFFFFF);
-      old[k] = 0xFFFFFFFFu;
-      if (pass[k]) old[k] = atomicOr(B.bitmap + (h[k] >> 5), 1u << (h[k] & 31u));
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (!pass[k]) continue;
-      const int32_t state = no[k].x & 0x7FFFFFFF;
-      if ((old[k] & (1u << (h[k] & 31u))) == 0) {
-        HVal mine;
-        mine.cost = (static_cast<unsigned long long>(c[k].y) << 32) | c[k].x;
-        mine.arg = (static_cast<unsigned long long>(c[k].z) << 32) | c[k].w;
-        const uint32_t pos =
-            register_claim(P, B, sh, h[k], state, no[k].x < 0 ? B.queue : nullptr, &sh.q_n[0]);
-        st_entry(B.table + h[k], mine, state, pos, ls.epoch);
-      } else {
-        const uint32_t slot = atomicAdd(&sh.park_n, 1u);
-        if (slot < kParkCap) {
-          parked[slot] = make_uint4(h[k], static_cast<uint32_t>(no[k].x), e + k * THREADS, 0u);
-        } else {
-          insert_arc(P, B, sh, ls.epoch, c[k].z,
-                     (static_cast<unsigned long long>(c[k].y) << 32) | c[k].x, c[k].w);
-        }
-      }
-    }
-  }
-  for (uint32_t e = tid; !defer && e < n_cand; e += THREADS) {
-#else
   for (uint32_t e = tid; e < n_cand; e += THREADS) {
-#endif
     const uint4 c = KD_OPT_CAND_CACHED ? __ldcg(B.cand + e) : __ldcs(B.cand + e);
     unsigned long long nk = (static_cast<unsigned long long>(c.y) << 32) | c.x;
     if (!(nk < cstar_key)) continue;  // faster-decoder.cc:211 / simple-decoder.cc:170, final cutoff
