@@ -11,11 +11,16 @@
 //   token list / Token  faster-decoder.h:110-156,
 //                       hash-list-inl.h:127-173     -> per-lane open-addressing
 //                       table (key = state, 128-bit value = ordered fp64 cost |
-//                       arc | backpointer) + frame-major backpointer arena
-//   InitDecoding        faster-decoder.cc:42-56     -> kd_init_kernel
+//                       arc | backpointer; entries claimed through an occupancy
+//                       bitmap) + frame-major backpointer arena, collected in place
+//   InitDecoding        faster-decoder.cc:42-56     -> first pass of a lane in
+//                                                      kd_advance_kernel, kd_init_kernel
 //   ReachedFinal /      faster-decoder.cc:347-354,
-//   GetBestPath         356-424                     -> kd_best_select_kernel,
-//                                                      kd_best_fill_kernel
+//   GetBestPath         356-424                     -> last pass of a lane in
+//                                                      kd_advance_kernel (lane_finalize),
+//                                                      kd_best_select_kernel,
+//                                                      kd_best_fill_kernel,
+//                                                      kd_reached_final_kernel
 //
 // Costs are fp64 sums of fp32 addends, added in the reference's order
 // ((w + cost) + ac, faster-decoder.cc:210), so they are bit-identical to the
@@ -24,17 +29,20 @@
 // running cutoff in shared memory only as a filter (anything admitted with
 // cost >= C* is ignored later), which makes the surviving token set exactly
 // {new_weight < C*}, independent of thread scheduling.  Equal-cost arrivals at
-// a state are resolved towards the lowest emitting-arc index (deterministic);
-// in the epsilon closure the incumbent stays (as in the reference).
+// a state are resolved towards the lowest emitting-arc index; in the epsilon
+// closure an incumbent from the emitting phase stays (as in the reference) and
+// equal-cost epsilon arrivals go to the lowest epsilon-arc index: every
+// backpointer is deterministic.
 //
-// What bounds the search (profiles/r1_*): not bandwidth but (a) the
-// dependent L2 round trips of a lane-frame, executed by 5 warps, (b) the work of the
-// 6 other lanes on the SM -- a lane alone runs 2.7x faster -- and (c) the instruction
-// cache: 7 lanes per SM are in 7 different phases of this kernel, and its body must stay
-// small (~3.5 k instructions; at 7 k a quarter of the issue cycles waited for fetches).
-// Hence: little unrolling, cold paths out of line, label tables so that a tenth of the
-// arcs is evaluated, candidates filtered by the exact cutoff before they touch the
-// table, a single-pass commit, and 32-byte table entries (one sector per state).
+// What bounds the search (profiles/r2_*): not bandwidth but (a) the
+// dependent memory round trips of a lane-frame (~24, plus ~27 barriers, whatever the
+// token count -- and half of the frames have fewer than 350 tokens), executed by 5
+// warps, (b) the work of the 6 other lanes on the SM, and (c) the instruction cache: 7
+// lanes per SM are in 7 different phases of this kernel, and its hot body must stay
+// small.  Hence: little unrolling, cold paths out of line, label tables so that a tenth
+// of the arcs is evaluated, candidates filtered by the exact cutoff before they touch
+// the table, first arrivals that write their whole entry with one 256-bit store, a
+// single-pass commit, the next frame's row fetched by a TMA bulk copy one frame ahead.
 #ifndef KD_KERNELS_CUH_
 #define KD_KERNELS_CUH_
 
