@@ -66,6 +66,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C3", choices=["C1", "C2", "C3", "C4"])
     ap.add_argument("--lanes", type=int, default=0, help="utterances per GPU (default: config)")
+    ap.add_argument("--total-utts", type=int, default=0,
+                    help="strong scaling (BASELINE config 5): this many utterances in total, "
+                         "sharded evenly over the ranks")
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--peak", type=float, default=12.0)
     ap.add_argument("--seed", type=int, default=3)
@@ -243,6 +246,17 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     lanes = args.lanes or CONFIG_LANES[args.config]
+    if args.total_utts:
+        if args.total_utts % world:
+            raise SystemExit("--total-utts must be a multiple of the number of ranks")
+        share = args.total_utts // world
+        lanes = min(share, lanes)
+        if share % lanes:
+            raise SystemExit("--total-utts: the per-rank share must be a multiple of --lanes")
+    # a step = `calls` launches of `lanes` utterances each (strong scaling: the rank's share of
+    # the job goes through the decoder's lane groups call after call, as a server would feed it)
+    calls = (args.total_utts // world) // lanes if args.total_utts else 1
+    scaling = "strong" if args.total_utts else "weak"
     T = args.frames
     cores = len(os.sched_getaffinity(0))
 
@@ -267,7 +281,7 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "impl": "reference",
             "config": {"workload": CONFIG_NAME[args.config], "peak": args.peak, "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
@@ -308,17 +322,17 @@ def main():
                            threads_per_lane=args.threads_per_lane or CONFIG_THREADS[args.config],
                            chunk_frames=args.chunk_frames)
     # every rank decodes its own utterances (seed differs per rank): weak scaling
-    logp = make_device_logprobs(g, lanes, T, args.seed + 7919 * rank, args.peak, dev)
+    logp = make_device_logprobs(g, lanes * calls, T, args.seed + 7919 * rank, args.peak, dev)
     torch.cuda.synchronize()
     groups = [list(range(k * lanes, (k + 1) * lanes)) for k in range(n_groups)]
     rows = [T] * lanes
-    dptrs = [logp[u].data_ptr() for u in range(lanes)]
+    dptrs = [[logp[c * lanes + u].data_ptr() for u in range(lanes)] for c in range(calls)]
     host = None
     if not args.no_e2e:
-        host = torch.empty((lanes, T, V), dtype=torch.float32, pin_memory=True)
+        host = torch.empty((lanes * calls, T, V), dtype=torch.float32, pin_memory=True)
         host.copy_(logp)
         torch.cuda.synchronize()
-        hptrs = [host[u].data_ptr() for u in range(lanes)]
+        hptrs = [[host[c * lanes + u].data_ptr() for u in range(lanes)] for c in range(calls)]
     setup_s = time.time() - t_setup
 
     result = {}
@@ -328,8 +342,8 @@ def main():
         `lanes` utterances in ONE kernel launch; step k+1 is enqueued before step k's paths
         are read (when there is more than one lane group)."""
         pending = []
-        for k in range(steps):
-            t = dec.advance_async(groups[k % n_groups], ptrs, rows, V, None, -1, mem_kind,
+        for k in range(steps * calls):
+            t = dec.advance_async(groups[k % n_groups], ptrs[k % calls], rows, V, None, -1, mem_kind,
                                   init=True, finalize=True)
             pending.append(t)
             if len(pending) >= n_groups:
@@ -368,9 +382,9 @@ def main():
     st = dec.stats()  # counters of the last step of every lane group (InitDecoding resets them)
     for k in st:
         if k != "max_tokens":
-            st[k] //= min(n_groups, args.steps + args.warmup + 1)
+            st[k] //= min(n_groups, (args.steps + args.warmup + 1) * calls)
     ms_per_step = dt / args.steps * 1e3
-    frames_per_step = lanes * T * world
+    frames_per_step = lanes * calls * T * world
     value = frames_per_step / (dt / args.steps)
     # launches of consecutive steps overlap: the device time per launch is the span from the
     # first launch's start to the last one's end, over the number of launches
@@ -397,11 +411,11 @@ def main():
         e2e = {"value": frames_per_step / (dt_h / args.steps), "unit": UNIT,
                # share of the lanes' time spent waiting for rows still on their way from the host
                "input_wait_frac": st_h["cycles_input_wait"] / max(1, busy_h + st_h["cycles_input_wait"]),
-               "h2d_bytes_per_step": int(lanes * T * V * 4), "d2h_bytes_per_step": d2h,
+               "h2d_bytes_per_step": int(lanes * calls * T * V * 4), "d2h_bytes_per_step": d2h * calls,
                "ms_per_step": dt_h / args.steps * 1e3,
                # what every rank's host link has to sustain; with several ranks uploading at
                # once this, not the search, bounds the end-to-end figure
-               "h2d_gb_per_s_per_rank": lanes * T * V * 4 / (dt_h / args.steps) / 1e9,
+               "h2d_gb_per_s_per_rank": lanes * calls * T * V * 4 / (dt_h / args.steps) / 1e9,
                "kernel_span_ms_per_step": span_h / max(1, n_launch_h)}
 
     cpu = None
@@ -410,7 +424,8 @@ def main():
         from oracle import kd_ref
         if kd_ref.available():
             n_s = n_keep
-            sample_mats = logp[:n_s].cpu().numpy()
+            # (the paths kept are those of the step's last call)
+            sample_mats = logp[(calls - 1) * lanes:(calls - 1) * lanes + n_s].cpu().numpy()
             rg = kd_ref.RefGraph(g)
             secs, rpaths, rrf = kd_ref.decode_batch(rg, sample_mats, kd_ref.Options(**OPTS), cores,
                                                     want_paths=True)
@@ -457,11 +472,12 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": CONFIG_NAME[args.config], "graph": g.stats(),
-                       "lanes_per_gpu": lanes, "frames": T, "vocab": V, "peak": args.peak,
+                       "lanes_per_gpu": lanes, "calls_per_step": calls,
+                       "total_utts": lanes * calls * world, "frames": T, "vocab": V, "peak": args.peak,
                        "options": OPTS, "parallelism": f"replicas x{world} (utterances sharded)",
-                       "l2_policy": "inputs larger than L2 (log-probs %.2f GB per GPU)" % (lanes * T * V * 4 / 1e9),
+                       "l2_policy": "inputs larger than L2 (log-probs %.2f GB per GPU)" % (lanes * calls * T * V * 4 / 1e9),
                        "threads_per_lane": dec.info()["threads_per_lane"],
                        "lane_groups": n_groups,
                        "pipelining": ("step k+1 enqueued before step k's paths are read; one "

@@ -143,6 +143,12 @@ KD_API int kd_decoder_create(kd_graph *g, const kd_options *opts,
 KD_API int kd_decoder_destroy(kd_decoder *d);
 /* FasterDecoder::SetOptions (faster-decoder.h:78) */
 KD_API int kd_decoder_set_options(kd_decoder *d, const kd_options *opts);
+/* Back to the state kd_decoder_create left it in -- every lane uninitialised, calls in flight
+ * completed and forgotten -- keeping the device buffers, streams and pinned memory: what a host
+ * wrapper calls to hand a decoder from one short-lived FasterDecoder object to the next (the
+ * reference's scripts construct one per utterance, faster-decoder.cc:21-32) instead of paying
+ * kd_decoder_destroy + kd_decoder_create each time. */
+KD_API int kd_decoder_reset(kd_decoder *d);
 
 /* FasterDecoder::InitDecoding (faster-decoder.cc:42-56) for n lanes. */
 KD_API int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes);

@@ -56,7 +56,9 @@ def build_pybind(force: bool = False) -> str:
     names = ["faster-decoder.cc", "simple-decoder.cc", "decodable-ctc.cc", "fst-io.cc",
              os.path.join("python", "module.cc")]
     srcs = [os.path.join(CSRC, n) for n in names]
-    hdrs = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith(".h")]
+    # every header below csrc/ (minifst/, kaldifst stand-ins, compat shims) and the C ABI
+    hdrs = [os.path.join(d, n) for d, _, fs in os.walk(CSRC) for n in fs if n.endswith(".h")]
+    hdrs.append(os.path.join(ROOT, "include", "kd_capi.h"))
     if not all(os.path.exists(s) for s in srcs):
         return ""
     if force or _newer(out, srcs + hdrs + [os.path.join(LIB_DIR, "libkd_b200.so")]):

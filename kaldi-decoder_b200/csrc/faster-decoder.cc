@@ -7,7 +7,11 @@
 #include "kaldi-decoder_b200/csrc/faster-decoder.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
 #include <cstdlib>
+#include <list>
+#include <mutex>
 #include <utility>
 
 #include "kaldi-decoder_b200/csrc/log.h"
@@ -47,6 +51,53 @@ kd_decoder_config ToC(const DeviceConfig &d, int32_t max_lanes) {
   return c;
 }
 
+// What makes two decoders of one graph interchangeable (DeviceGraph::TakeIdle / PutIdle).
+std::string IdleKey(const kd_decoder_config &c) {
+  char buf[128];
+  std::snprintf(buf, sizeof(buf), "%d/%d/%d/%lld/%d/%d", c.search, c.max_lanes, c.hash_capacity,
+                static_cast<long long>(c.arena_records), c.threads_per_lane, c.chunk_frames);
+  return buf;
+}
+
+// ContentId() of FST types that have one (minifst), 0 otherwise (OpenFst: no graph sharing).
+template <class F>
+auto ContentIdOf(const F &f, int) -> decltype(static_cast<uint64_t>(f.ContentId())) {
+  return f.ContentId();
+}
+template <class F>
+uint64_t ContentIdOf(const F &, long) {
+  return 0;
+}
+
+struct GraphCache {
+  struct Slot {
+    uint64_t content;
+    int32_t device;
+    std::shared_ptr<DeviceGraph> graph;
+  };
+  std::mutex mu;
+  std::list<Slot> slots;  // most recently used first
+};
+
+// (never destroyed: at process exit the CUDA runtime may already be gone)
+GraphCache &TheGraphCache() {
+  static GraphCache *c = new GraphCache;
+  return *c;
+}
+
+size_t GraphCacheSize() {
+  if (const char *e = std::getenv("KD_B200_GRAPH_CACHE")) return static_cast<size_t>(std::max(0, std::atoi(e)));
+  return 4;
+}
+
+// how many idle decoders a graph keeps for the next decoder objects (0 = none: destroy at once)
+size_t MaxIdleDecoders() {
+  if (const char *e = std::getenv("KD_B200_IDLE_DECODERS")) return static_cast<size_t>(std::max(0, std::atoi(e)));
+  return 16;
+}
+
+std::atomic<int64_t> g_uploads{0};
+
 // Linear lattice from the raw per-token arcs, then RemoveEpsLocal, as
 // faster-decoder.cc:408-422 of the reference.
 void BuildLattice(int64_t n, const int32_t *il, const int32_t *ol, const float *gw,
@@ -68,7 +119,13 @@ void BuildLattice(int64_t n, const int32_t *il, const int32_t *ol, const float *
 
 // --------------------------------------------------------------- DeviceGraph
 
-DeviceGraph::DeviceGraph(const fst::Fst<fst::StdArc> &fst, int32_t device) : device_(device) {
+struct DeviceGraph::Idle {
+  std::mutex mu;
+  std::vector<std::pair<std::string, kd_decoder *>> list;
+};
+
+DeviceGraph::DeviceGraph(const fst::Fst<fst::StdArc> &fst, int32_t device)
+    : device_(device), idle_(new Idle) {
   // Only what OpenFst's abstract Fst<Arc> offers: CountStates, Start, Final, ArcIterator
   // (NumStates() lives on ExpandedFst; the reference binds `const Fst<StdArc>&`).
   const int32_t n = fst::CountStates(fst);
@@ -90,21 +147,85 @@ DeviceGraph::DeviceGraph(const fst::Fst<fst::StdArc> &fst, int32_t device) : dev
   Check(kd_graph_create(device, n, fst.Start(), off.data(), il.data(), ol.data(), w.data(),
                         ns.data(), fin.data(), &g));
   handle_ = g;
+  g_uploads.fetch_add(1, std::memory_order_relaxed);
 }
 
-DeviceGraph::~DeviceGraph() { kd_graph_destroy(static_cast<kd_graph *>(handle_)); }
+int64_t DeviceGraph::NumUploads() { return g_uploads.load(std::memory_order_relaxed); }
+
+DeviceGraph::~DeviceGraph() {
+  for (auto &e : idle_->list) kd_decoder_destroy(e.second);
+  kd_graph_destroy(static_cast<kd_graph *>(handle_));
+}
+
+std::shared_ptr<DeviceGraph> DeviceGraph::Shared(const fst::Fst<fst::StdArc> &fst, int32_t device) {
+  const uint64_t content = ContentIdOf(fst, 0);
+  const size_t keep = GraphCacheSize();
+  if (content == 0 || keep == 0) return std::make_shared<DeviceGraph>(fst, device);
+  GraphCache &c = TheGraphCache();
+  // (held across the upload: a second thread that wants the same graph waits for it)
+  std::lock_guard<std::mutex> lock(c.mu);
+  for (auto it = c.slots.begin(); it != c.slots.end(); ++it) {
+    if (it->content == content && it->device == device) {
+      c.slots.splice(c.slots.begin(), c.slots, it);
+      return c.slots.front().graph;
+    }
+  }
+  auto g = std::make_shared<DeviceGraph>(fst, device);
+  c.slots.push_front({content, device, g});
+  while (c.slots.size() > keep) c.slots.pop_back();
+  return g;
+}
+
+void DeviceGraph::ClearCache() {
+  GraphCache &c = TheGraphCache();
+  std::list<GraphCache::Slot> drop;
+  {
+    std::lock_guard<std::mutex> lock(c.mu);
+    drop.swap(c.slots);
+  }
+}
+
+void *DeviceGraph::TakeIdle(const std::string &key) {
+  std::lock_guard<std::mutex> lock(idle_->mu);
+  for (size_t i = idle_->list.size(); i-- > 0;) {
+    if (idle_->list[i].first == key) {
+      kd_decoder *d = idle_->list[i].second;
+      idle_->list.erase(idle_->list.begin() + static_cast<long>(i));
+      return d;
+    }
+  }
+  return nullptr;
+}
+
+void DeviceGraph::PutIdle(const std::string &key, void *decoder) {
+  auto *d = static_cast<kd_decoder *>(decoder);
+  if (!d) return;
+  const size_t keep = MaxIdleDecoders();
+  if (keep > 0 && kd_decoder_reset(d) == KD_OK) {
+    std::lock_guard<std::mutex> lock(idle_->mu);
+    if (idle_->list.size() < keep) {
+      idle_->list.emplace_back(key, d);
+      return;
+    }
+  }
+  kd_decoder_destroy(d);
+}
 
 // ------------------------------------------------------------- FasterDecoder
 
 struct FasterDecoder::Impl {
   std::shared_ptr<DeviceGraph> graph;
   kd_decoder *dec = nullptr;
+  std::string idle_key;
   std::vector<float> scratch;  // materialised generic decodables
-  ~Impl() { kd_decoder_destroy(dec); }
+  // the device side outlives this object: the next FasterDecoder of the graph takes it over
+  ~Impl() {
+    if (dec) graph->PutIdle(idle_key, dec);
+  }
 };
 
 FasterDecoder::FasterDecoder(const fst::Fst<fst::StdArc> &fst, const FasterDecoderOptions &config)
-    : FasterDecoder(std::make_shared<DeviceGraph>(fst, 0), config, DeviceConfig()) {}
+    : FasterDecoder(DeviceGraph::Shared(fst, 0), config, DeviceConfig()) {}
 
 FasterDecoder::FasterDecoder(std::shared_ptr<DeviceGraph> graph,
                              const FasterDecoderOptions &config, const DeviceConfig &dev)
@@ -112,6 +233,12 @@ FasterDecoder::FasterDecoder(std::shared_ptr<DeviceGraph> graph,
   impl_->graph = std::move(graph);
   kd_options o = ToC(config);
   kd_decoder_config c = ToC(dev, 1);
+  impl_->idle_key = IdleKey(c);
+  impl_->dec = static_cast<kd_decoder *>(impl_->graph->TakeIdle(impl_->idle_key));
+  if (impl_->dec) {
+    Check(kd_decoder_set_options(impl_->dec, &o));  // (on failure ~Impl puts it back)
+    return;
+  }
   Check(kd_decoder_create(static_cast<kd_graph *>(impl_->graph->Handle()), &o, &c, &impl_->dec));
 }
 
@@ -217,7 +344,7 @@ struct BatchFasterDecoder::Impl {
 BatchFasterDecoder::BatchFasterDecoder(const fst::Fst<fst::StdArc> &fst,
                                        const FasterDecoderOptions &config, int32_t max_lanes,
                                        const DeviceConfig &dev)
-    : BatchFasterDecoder(std::make_shared<DeviceGraph>(fst, dev.device), config, max_lanes, dev) {}
+    : BatchFasterDecoder(DeviceGraph::Shared(fst, dev.device), config, max_lanes, dev) {}
 
 BatchFasterDecoder::BatchFasterDecoder(std::shared_ptr<DeviceGraph> graph,
                                        const FasterDecoderOptions &config, int32_t max_lanes,

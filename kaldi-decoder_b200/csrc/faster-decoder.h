@@ -80,9 +80,28 @@ class DeviceGraph {
   void *Handle() const { return handle_; }
   int32_t Device() const { return device_; }
 
+  // The device copy of `fst`, shared by all decoders that are built from the same FST content.
+  // Scripts in the reference's style construct a FasterDecoder from the HLG for every utterance
+  // (the reference's constructor only stores a reference, faster-decoder.cc:21-32); with this
+  // only the first one converts and uploads the graph.  It needs an FST type that can identify
+  // its content (minifst: Fst::ContentId(), which changes when the FST is modified); any other
+  // type is uploaded afresh on every call.  The last few graphs are kept alive (environment
+  // KD_B200_GRAPH_CACHE = how many, default 4, 0 = no sharing); ClearCache() lets go of them.
+  static std::shared_ptr<DeviceGraph> Shared(const fst::Fst<fst::StdArc> &fst, int32_t device = 0);
+  static void ClearCache();
+  static int64_t NumUploads();  // graphs converted and copied to a device so far (diagnostics)
+
+  // Idle decoders (kd_decoder*) of this graph, handed from one decoder object to the next one
+  // with the same capacities (`key`); PutIdle resets the decoder (or destroys it if enough are
+  // waiting already).
+  void *TakeIdle(const std::string &key);
+  void PutIdle(const std::string &key, void *decoder);
+
  private:
+  struct Idle;
   void *handle_ = nullptr;
   int32_t device_ = 0;
+  std::unique_ptr<Idle> idle_;
 };
 
 class FasterDecoder {

@@ -993,6 +993,24 @@ int kd_decoder_set_options(kd_decoder *d, const kd_options *opts) {
   return KD_OK;
 }
 
+int kd_decoder_reset(kd_decoder *d) {
+  if (!d) return Fail(KD_ERR_INVALID, "decoder is null");
+  WaitAll(d);  // (the outcome of calls nobody waited for goes with them)
+  for (int32_t l = 0; l < d->max_lanes; ++l) {
+    d->frames[l] = -1;
+    d->status[l] = 0;
+    d->bp_valid[l] = 0;
+    d->use_final[l] = 1;
+    d->rf_cache[l] = -1;
+    d->lane_slot[l] = -1;
+  }
+  for (int i = 0; i < kNumSlots; ++i) {
+    d->slots[i].rc = KD_OK;
+    d->slots[i].msg.clear();
+  }
+  return KD_OK;
+}
+
 int kd_decoder_init(kd_decoder *d, int32_t n, const int32_t *lanes) {
   int rc = CheckLanes(d, n, lanes);
   if (rc) return rc;

@@ -26,6 +26,7 @@
 
 #include <sys/types.h>
 
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <limits>
@@ -127,6 +128,39 @@ struct StateIteratorData {
   typename A::StateId nstates = 0;
 };
 
+// Identifies the CONTENT an FST object holds, for caches keyed on "exactly this graph" (the
+// device copy of a decoding graph, faster-decoder.cc): a process-unique number the object gets
+// the first time it is asked, keeps while it is only read, hands to its copies, and drops when it
+// is modified.  (minifst only: OpenFst has no such thing, and code that must also build against
+// OpenFst detects ContentId() before using it.)
+class ContentTag {
+ public:
+  ContentTag() = default;
+  ContentTag(const ContentTag &o) : id_(o.id_.load(std::memory_order_relaxed)) {}
+  ContentTag(ContentTag &&o) noexcept : id_(o.id_.exchange(0, std::memory_order_relaxed)) {}
+  ContentTag &operator=(const ContentTag &o) {
+    id_.store(o.id_.load(std::memory_order_relaxed), std::memory_order_relaxed);
+    return *this;
+  }
+  ContentTag &operator=(ContentTag &&o) noexcept {
+    if (this != &o) id_.store(o.id_.exchange(0, std::memory_order_relaxed), std::memory_order_relaxed);
+    return *this;
+  }
+  uint64_t Get() const {
+    uint64_t v = id_.load(std::memory_order_relaxed);
+    if (v == 0) {
+      static std::atomic<uint64_t> next{1};
+      const uint64_t fresh = next.fetch_add(1, std::memory_order_relaxed);
+      v = id_.compare_exchange_strong(v, fresh, std::memory_order_relaxed) ? fresh : v;
+    }
+    return v;
+  }
+  void Drop() { id_.store(0, std::memory_order_relaxed); }
+
+ private:
+  mutable std::atomic<uint64_t> id_{0};
+};
+
 // Abstract read-only FST.
 template <class A>
 class Fst {
@@ -136,6 +170,20 @@ class Fst {
   using Weight = typename A::Weight;
 
   virtual ~Fst() = default;
+
+  // see ContentTag; two objects with the same ContentId() hold the same states and arcs
+  uint64_t ContentId() const { return content_.Get(); }
+
+ protected:
+  // every mutator of a derived class calls this (MutableArcs() too: its caller is about to write)
+  void ContentChanged() { content_.Drop(); }
+  // for converting constructors: this object now holds exactly what `other` holds
+  void SameContentAs(const Fst &other) { content_ = other.content_; }
+
+ private:
+  ContentTag content_;
+
+ public:
 
   virtual StateId Start() const = 0;
   virtual Weight Final(StateId s) const = 0;
@@ -207,29 +255,45 @@ class VectorFst : public MutableFst<A> {
   }
 
   void DeleteStates() override {
+    this->ContentChanged();
     states_.clear();
     start_ = kNoStateId;
   }
   StateId AddState() override {
+    this->ContentChanged();
     states_.emplace_back();
     return static_cast<StateId>(states_.size() - 1);
   }
-  void SetStart(StateId s) override { start_ = s; }
+  void SetStart(StateId s) override {
+    this->ContentChanged();
+    start_ = s;
+  }
   void AddArc(StateId s, const A &arc) override {
+    this->ContentChanged();
     states_.at(s).arcs.push_back(arc);
   }
-  void SetFinal(StateId s, Weight w) override { states_.at(s).final = w; }
+  void SetFinal(StateId s, Weight w) override {
+    this->ContentChanged();
+    states_.at(s).final = w;
+  }
   void ReserveArcs(StateId s, size_t n) override {
     states_.at(s).arcs.reserve(n);
   }
-  void DeleteArcs(StateId s) override { states_.at(s).arcs.clear(); }
-  A *MutableArcs(StateId s) override { return states_.at(s).arcs.data(); }
+  void DeleteArcs(StateId s) override {
+    this->ContentChanged();
+    states_.at(s).arcs.clear();
+  }
+  A *MutableArcs(StateId s) override {
+    this->ContentChanged();
+    return states_.at(s).arcs.data();
+  }
 
   void ReserveStates(size_t n) { states_.reserve(n); }
 
   // Keeps only the states with keep[s] == true, renumbering the survivors in
   // increasing order of their old ids and dropping arcs into removed states.
   void KeepStates(const std::vector<bool> &keep) {
+    this->ContentChanged();
     std::vector<StateId> renumber(states_.size(), kNoStateId);
     StateId n = 0;
     for (size_t s = 0; s < states_.size(); ++s) {
@@ -273,6 +337,7 @@ class VectorFst : public MutableFst<A> {
       other.InitArcIterator(s, &d);
       states_[s].arcs.assign(d.arcs, d.arcs + d.narcs);
     }
+    this->SameContentAs(other);
   }
 
   StateId start_ = kNoStateId;
@@ -305,6 +370,7 @@ class ConstFst : public ExpandedFst<A> {
       arcs_.insert(arcs_.end(), d.arcs, d.arcs + d.narcs);
       offsets_.push_back(arcs_.size());
     }
+    this->SameContentAs(other);
   }
 
   // Takes ownership of pre-built CSR arrays.  offsets.size() == finals.size()+1

@@ -135,7 +135,11 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       .def("to_str", [](const fst::StdFst &f) { return WriteFstText(f); })
       .def("write", [](const fst::StdFst &f, const std::string &p) { WriteFst(f, p); },
            py::arg("filename"), "OpenFst binary, fst type \"vector\"")
-      .def_property_readonly("fst_type", [](const fst::StdFst &f) { return f.Type(); });
+      .def_property_readonly("fst_type", [](const fst::StdFst &f) { return f.Type(); })
+      .def_property_readonly("content_id", &fst::StdFst::ContentId,
+                             "process-unique number of the states and arcs this object holds "
+                             "(copies share it, a modification replaces it); decoders built from "
+                             "FSTs with the same content_id share one device graph");
 
   py::class_<fst::StdVectorFst, fst::StdFst>(m, "StdVectorFst")
       .def(py::init<>())
@@ -144,7 +148,18 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
                   py::arg("row_offsets"), py::arg("ilabel"), py::arg("olabel"), py::arg("weight"),
                   py::arg("nextstate"), py::arg("final"))
       .def_static("read", &ReadFst, py::arg("filename"))
-      .def_static("from_str", &ReadFstText, py::arg("s"), py::arg("acceptor") = false);
+      .def_static("from_str", &ReadFstText, py::arg("s"), py::arg("acceptor") = false)
+      .def("add_state", &fst::StdVectorFst::AddState)
+      .def("set_start", &fst::StdVectorFst::SetStart, py::arg("state"))
+      .def("set_final",
+           [](fst::StdVectorFst &f, int s, float w) { f.SetFinal(s, fst::StdArc::Weight(w)); },
+           py::arg("state"), py::arg("weight") = 0.0f)
+      .def("add_arc",
+           [](fst::StdVectorFst &f, int s, int il, int ol, float w, int ns) {
+             f.AddArc(s, fst::StdArc(il, ol, fst::StdArc::Weight(w), ns));
+           },
+           py::arg("state"), py::arg("ilabel"), py::arg("olabel"), py::arg("weight"),
+           py::arg("nextstate"));
 
   // Immutable CSR form: what an OpenFst "const" file holds and what the device graph is
   // built from without an intermediate copy per state.
@@ -456,6 +471,11 @@ PYBIND11_MODULE(_kaldi_decoder, m) {
       py::arg("ilabels"), py::arg("olabels"), py::arg("graph"), py::arg("acoustic"),
       py::arg("final"));
 
+  m.def("graph_uploads", &DeviceGraph::NumUploads,
+        "How many graphs this process has converted and copied to a GPU so far.");
+  m.def("clear_graph_cache", &DeviceGraph::ClearCache,
+        "Lets go of the device graphs kept for decoders that are constructed from an FST "
+        "(DeviceGraph::Shared); graphs still used by a decoder live on until it is gone.");
   m.def("device_count", []() {
     int n = 0;
     kd_device_count(&n);

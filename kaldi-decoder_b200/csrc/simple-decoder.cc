@@ -30,7 +30,7 @@ struct SimpleDecoder::Impl {
 };
 
 SimpleDecoder::SimpleDecoder(const fst::Fst<fst::StdArc> &fst, float beam)
-    : SimpleDecoder(std::make_shared<DeviceGraph>(fst, 0), beam, DeviceConfig()) {}
+    : SimpleDecoder(DeviceGraph::Shared(fst, 0), beam, DeviceConfig()) {}
 
 SimpleDecoder::SimpleDecoder(std::shared_ptr<DeviceGraph> graph, float beam,
                              const DeviceConfig &dev)

@@ -33,8 +33,10 @@ try:
         StdConstFst,
         StdFst,
         StdVectorFst,
+        clear_graph_cache,
         device_count,
         get_linear_symbol_sequence,
+        graph_uploads,
     )
 except ImportError as e:  # pragma: no cover
     raise ImportError(

@@ -52,7 +52,7 @@ class KdStats(C.Structure):
 
 EXPORTED = (
     "kd_last_error", "kd_device_count", "kd_graph_create", "kd_graph_destroy", "kd_graph_info",
-    "kd_decoder_create", "kd_decoder_destroy", "kd_decoder_set_options", "kd_decoder_init",
+    "kd_decoder_create", "kd_decoder_destroy", "kd_decoder_set_options", "kd_decoder_reset", "kd_decoder_init",
     "kd_decoder_advance", "kd_decoder_num_frames_decoded", "kd_decoder_reached_final",
     "kd_decoder_best_path_prepare", "kd_decoder_best_path_fetch", "kd_decoder_best_path_view",
     "kd_decoder_best_path",
@@ -81,6 +81,7 @@ def lib():
         L.kd_decoder_create.argtypes = [vp, C.POINTER(KdOptions), C.POINTER(KdConfig), C.POINTER(vp)]
         L.kd_decoder_destroy.argtypes = [vp]
         L.kd_decoder_set_options.argtypes = [vp, C.POINTER(KdOptions)]
+        L.kd_decoder_reset.argtypes = [vp]
         L.kd_decoder_init.argtypes = [vp, i32, vp]
         L.kd_decoder_advance.argtypes = [vp, i32, vp, vp, vp, i32, vp, i32, C.c_int]
         L.kd_decoder_num_frames_decoded.argtypes = [vp, i32, C.POINTER(i32)]
@@ -253,6 +254,10 @@ class LaneDecoder:
 
     def set_options(self, opts: KdOptions):
         _check(lib().kd_decoder_set_options(self.h, C.byref(opts)))
+
+    def reset(self):
+        """Every lane uninitialised again, as after creation; buffers and streams are kept."""
+        _check(lib().kd_decoder_reset(self.h))
 
     def init(self, lanes):
         la = self._lanes(lanes)

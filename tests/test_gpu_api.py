@@ -468,6 +468,54 @@ def test_single_utterance_decoders_run_concurrently_from_python_threads():
     assert not errors, errors
 
 
+def test_a_decoder_per_utterance_shares_the_graph_and_recycles_the_device_side():
+    """The reference's scripts construct `FasterDecoder(HLG, opts)` for every utterance
+    (its constructor only stores a reference, faster-decoder.cc:21-32).  Here decoders built from
+    the same FST content share ONE device graph, and a decoder that goes away hands its device
+    buffers to the next one -- which must behave exactly like a new decoder."""
+    import kaldi_decoder as kd
+    gc = GoldenCase("hlg300_peaky")
+    g = gc.graph
+    o = gc.opts
+    vfst = kd.StdVectorFst.from_arrays(g.num_states, g.start, g.row_off, g.ilabel, g.olabel,
+                                       g.weight, g.nextstate, g.final)
+    opts = kd.FasterDecoderOptions(beam=o["beam"], max_active=o["max_active"], min_active=o["min_active"])
+    kd.clear_graph_cache()
+    before = kd.graph_uploads()
+    for u in range(min(4, gc.n_utts)):
+        dec = kd.FasterDecoder(vfst, opts)       # as icefall's decode(): one object per utterance
+        assert dec.num_frames_decoded() == -1    # a recycled device side starts uninitialised ...
+        with pytest.raises(RuntimeError):        # ... and says so (faster-decoder.cc:128-129)
+            dec.advance_decoding(kd.DecodableCtc(gc.logp(u)))
+        dec.decode(kd.DecodableCtc(gc.logp(u)))
+        want = gc.best(u, True)
+        assert dec.reached_final() == gc.reached_final(u)
+        ok, best = dec.get_best_path()
+        assert ok == want.ok
+        assert kd.get_linear_symbol_sequence(best)[2] == [int(x) for x in want.osyms]
+        del dec
+    assert kd.graph_uploads() == before + 1
+    # copies and conversions hold the same content: no new upload
+    dec = kd.FasterDecoder(kd.StdConstFst(vfst), opts)
+    assert kd.graph_uploads() == before + 1
+    # invalid options on a recycled decoder raise as on a new one, and do not lose it
+    del dec
+    with pytest.raises(RuntimeError):
+        kd.FasterDecoder(vfst, kd.FasterDecoderOptions(max_active=1))
+    # a modified FST is a different graph
+    edited = kd.StdVectorFst(vfst)
+    s_new = edited.add_state()
+    edited.add_arc(s_new, 1, 1, 0.25, s_new)
+    assert edited.content_id != vfst.content_id
+    dec = kd.FasterDecoder(edited, opts)
+    assert kd.graph_uploads() == before + 2
+    dec.decode(kd.DecodableCtc(gc.logp(0)))      # (the new state is unreachable: same answer)
+    assert kd.get_linear_symbol_sequence(dec.get_best_path()[1])[2] == [int(x) for x in gc.best(0).osyms]
+    kd.clear_graph_cache()
+    dec2 = kd.FasterDecoder(vfst, opts)
+    assert kd.graph_uploads() == before + 3
+
+
 def test_cpp_caller_written_against_the_reference_headers_runs(tmp_path):
     """The C++ drop-in caller (tests/cpp/drop_in.cc: the reference's include paths, Decode /
     InitDecoding + AdvanceDecoding / GetBestPath / ReachedFinal / NumFramesDecoded) against

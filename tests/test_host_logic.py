@@ -308,6 +308,30 @@ def test_const_and_vector_fst_types_and_constructor_overloads():
         kd.FasterDecoder("not an fst", opts)
 
 
+def test_fst_content_id_follows_the_content_not_the_object():
+    """Decoders built from FSTs with the same content_id share one device graph
+    (DeviceGraph::Shared): the id must survive copies and conversions, and must not survive a
+    modification -- the reference reads its `const Fst&` at decode time, so a stale device copy
+    would be a silent difference."""
+    import kaldi_decoder as kd
+    g = small_graph("HL")
+    args = (g.num_states, g.start, g.row_off, g.ilabel, g.olabel, g.weight, g.nextstate, g.final)
+    v = kd.StdVectorFst.from_arrays(*args)
+    same = v.content_id
+    assert same != 0 and v.content_id == same                      # reading does not change it
+    assert kd.StdVectorFst.from_arrays(*args).content_id != same   # equal arcs, another object: no claim
+    assert kd.StdConstFst(v).content_id == same                    # conversions hold the same content
+    assert kd.StdVectorFst(kd.StdConstFst(v)).content_id == same
+    w = kd.StdVectorFst(v)
+    for edit in (lambda f: f.add_state(), lambda f: f.set_start(1), lambda f: f.set_final(0, 1.5),
+                 lambda f: f.add_arc(0, 1, 2, 0.5, 1)):
+        before = w.content_id
+        edit(w)
+        assert w.content_id != before and w.content_id != same
+    assert v.content_id == same                                    # the source of the copy is untouched
+    assert w.num_states == v.num_states + 1 and w.start == 1 and w.final(0) == 1.5
+
+
 def test_host_sources_compile_against_an_openfst_shaped_fst_h(tmp_path):
     """with OpenFst on the include path, csrc/minifst/fst is dropped.  The
     host sources are syntax-checked against tests/openfst_shape (OpenFst's Fst / ExpandedFst /
