@@ -71,6 +71,12 @@
 #ifndef KD_OPT_DEFER
 #define KD_OPT_DEFER 1         // arrivals at states already in the table are recombined in a second pass
 #endif
+#ifndef KD_OPT_COARSE
+#define KD_OPT_COARSE 1       // item -> token search: top level in its own bank-conflict-free array
+#endif
+#ifndef KD_OPT_ST256
+#define KD_OPT_ST256 1        // state records loaded with one 256-bit load
+#endif
 #ifndef KD_OPT_SLIST
 #define KD_OPT_SLIST 1        // head of the frame's slot list in shared memory
 #endif
@@ -350,6 +356,19 @@ __device__ __forceinline__ int2 gld(const int2 *p) {
 #endif
 }
 
+// a 32-byte state record in one 256-bit load (one L1 tag lookup instead of two)
+__device__ __forceinline__ void gld_state(const int4 *p, int4 *a, int4 *b) {
+#if KD_OPT_ST256 && KD_OPT_GRAPH_EL
+  asm volatile("ld.global.nc.L2::cache_hint.v8.s32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+               : "=r"(a->x), "=r"(a->y), "=r"(a->z), "=r"(a->w), "=r"(b->x), "=r"(b->y), "=r"(b->z),
+                 "=r"(b->w)
+               : "l"(p), "l"(l2_evict_last()));
+#else
+  *a = gld(p);
+  *b = gld(p + 1);
+#endif
+}
+
 // 128-bit compare-and-swap (ATOMG.E.CAS.128); returns the previous value.
 __device__ __forceinline__ HVal cas_hval(HVal *p, HVal cmp, HVal val) {
   HVal out;
@@ -431,6 +450,7 @@ struct Shared {
   unsigned long long red_k[2][16];  // block_min: per-warp minima, two buffers used alternately
   uint32_t hist[256];
   uint32_t warp_sums[32];
+  uint32_t ex_coarse[33];  // t_ex[32 * q]: the top level of the item -> token search, bank by bank
   long long t_mark;
   uint32_t cut_fkey;  // running next-frame cutoff, rounded UP to float (a filter only)
   uint32_t acc_emit, acc_eps, acc_expanded;  // per-frame counters
@@ -1251,8 +1271,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // arrives while the row is staged and the labels are ordered
   int4 seed_sa = make_int4(0, 0, 0, 0), seed_sb = make_int4(-1, 0, 0, 0);
   if (n > 0 && ls.best_state >= 0) {
-    seed_sa = gld(P.st + 2 * static_cast<size_t>(ls.best_state));
-    seed_sb = gld(P.st + 2 * static_cast<size_t>(ls.best_state) + 1);
+    gld_state(P.st + 2 * static_cast<size_t>(ls.best_state), &seed_sa, &seed_sb);
   }
   // The row is kept as it comes (log-probs); every use negates it (faster-decoder.cc:209).
   // Usually it is already on its way: the previous frame started a bulk copy (TMA) of it
@@ -1446,8 +1465,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         sa[k] = make_int4(0, 0, 0, 0);
         sb[k] = make_int4(-1, 0, 0, 0);
         if (ts[k] >= 0) {
-          sa[k] = gld(P.st + 2 * static_cast<size_t>(ts[k]));
-          sb[k] = gld(P.st + 2 * static_cast<size_t>(ts[k]) + 1);
+          gld_state(P.st + 2 * static_cast<size_t>(ts[k]), &sa[k], &sb[k]);
         }
       }
       // a valid bound on this frame's final cutoff (the seeded running cutoff)
@@ -1512,6 +1530,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     for (int k = 0; k < KT; ++k) {
       if (cnt[k] != 0) {
         t_ex[ex_toks] = ex_arcs;
+        if (KD_OPT_COARSE && TT <= 1024 && (ex_toks & 31u) == 0) sh.ex_coarse[ex_toks >> 5] = ex_arcs;
         t_beg[ex_toks] = beg[k] | (tab[k] >= 0 ? kLookupFlag : 0u);
         t_tab[ex_toks] = tab[k];
         t_cost[ex_toks] = tc[k];
@@ -1553,7 +1572,11 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
 #pragma unroll
           for (uint32_t stride = kSearchTop; stride; stride >>= 5) {
             const uint32_t pos = t_lo + lane * stride;
-            const bool le = pos < n_comp && t_ex[pos] <= jb;
+            // (the 32 probes of the stride-32 level would all fall into one bank of t_ex:
+            // that level reads its own copy, one word per lane)
+            const bool le =
+                pos < n_comp &&
+                ((KD_OPT_COARSE && TT <= 1024 && stride == 32) ? sh.ex_coarse[pos >> 5] : t_ex[pos]) <= jb;
             t_lo += (__popc(__ballot_sync(0xFFFFFFFFu, le)) - 1u) * stride;
           }
           // item -> token: bit mask of the token boundaries (first item index of the 32
