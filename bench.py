@@ -393,6 +393,7 @@ def main():
     alg_bytes = algorithmic_bytes(st, V)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     touched = touched_bytes(st, V)
+    traffic_now = measured_traffic(args.config, args.peak, lanes, T)
     paths = result["paths"]
     d2h = int(paths.d2h_bytes) + int(lanes * 256)  # parked paths + lane states
     n_final = int(np.count_nonzero(paths.reached_final))
@@ -489,11 +490,19 @@ def main():
             "gpu_launches": gpu_launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs,
-                         "traffic": measured_traffic(args.config, args.peak, lanes, T),
+                         "traffic": traffic_now,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu "
                                          "--set full capture of this build "
                                          "(profiles/r2_dram_bytes.json, per lane-frame x lanes x "
                                          "frames); null = no capture for this config",
+                         "traffic_gb_per_s": (traffic_now / (k_ms * 1e-3) / 1e9
+                                              if traffic_now and k_ms > 0 else None),
+                         "random_sector_peak": {"read": 1409.0, "write": 1128.0, "mixed": 1105.0,
+                                                "unit": "GB/s",
+                                                "note": "independent random 32-byte sectors over 8 GB "
+                                                        "on this GPU type (tools/hbm_random.cu, "
+                                                        "profiles/r2_hbm_random_sectors.txt): about "
+                                                        "half of `traffic` is of this kind"},
                          "kernel": "kd_advance_kernel", "kernel_ms": k_ms,
                          "kernel_ms_note": "launches of consecutive steps overlap: (end of the "
                                            "last launch - start of the first) / launches, CUDA "
