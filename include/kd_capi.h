@@ -114,6 +114,10 @@ typedef struct kd_stats {
   int64_t cycles_input_wait; /* SM cycles lanes spent waiting for log-prob rows still on their
                               way from the host (KD_MEM_HOST): the share of the search time
                               that the upload, not the search, decides                */
+  int64_t table_retries;   /* frames searched twice: a frame hashes into a region of the lane's
+                              table sized from its candidates (locality); when the epsilon
+                              closure fills that region the frame starts over with the whole
+                              table                                                    */
 } kd_stats;
 
 KD_API const char *kd_last_error(void);

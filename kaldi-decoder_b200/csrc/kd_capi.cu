@@ -120,6 +120,7 @@ struct kd_decoder {
   int32_t threads = 0;  // 0 = auto per launch
   int32_t simple = 0;   // KD_SEARCH_SIMPLE
   int32_t chunk_frames = 128;
+  uint32_t region_f = 16, region_min = 16384;  // per-frame table region (kd::Params)
   size_t device_bytes = 0;
   size_t l2_window_bytes = 0, l2_persist_bytes = 0;
 
@@ -220,6 +221,8 @@ kd::Params MakeParams(const kd_decoder *d) {
   int lg = 0;
   while ((1u << lg) < d->hcap) ++lg;
   P.hshift = 34 - lg;  // (lg - 2) scattered group bits, 2 in-group bits
+  P.region_f = d->region_f;
+  P.region_min = d->region_min;
   return P;
 }
 
@@ -628,6 +631,19 @@ int kd_decoder_create(kd_graph *g, const kd_options *opts, const kd_decoder_conf
   d->threads = c.threads_per_lane > 0 ? c.threads_per_lane : 0;
   d->simple = c.search == KD_SEARCH_SIMPLE ? 1 : 0;
   d->chunk_frames = c.chunk_frames > 0 ? c.chunk_frames : 128;
+  // KD_B200_TABLE_REGION="F,MIN": entries per candidate and smallest size of a frame's table
+  // region (measured default 16,16384; "0" = always the whole table; tiny values make most
+  // frames start over, which is how the tests exercise that path)
+  if (const char *e = getenv("KD_B200_TABLE_REGION")) {
+    unsigned f = 0, m = 0;
+    const int got = sscanf(e, "%u%*1[,:]%u", &f, &m);  // "F,MIN" or "F:MIN"
+    if (got >= 1) d->region_f = f;
+    if (got >= 2) {
+      uint32_t p = 64;
+      while (p < m && p < (1u << 30)) p <<= 1;
+      d->region_min = p;
+    }
+  }
 
   const size_t L = static_cast<size_t>(d->max_lanes);
   const size_t table_bytes_per_lane =
@@ -1695,6 +1711,7 @@ int kd_decoder_stats(kd_decoder *d, int32_t lane, kd_stats *out) {
     out->cycles_scan += L.cyc_scan;
     out->arena_compactions += L.st_compactions;
     out->cycles_input_wait += L.cyc_wait;
+    out->table_retries += L.st_redo;
   }
   return KD_OK;
 }

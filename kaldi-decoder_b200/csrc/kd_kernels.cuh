@@ -174,7 +174,7 @@ struct __align__(16) LaneState {
   long long st_compactions;  // arena garbage collections
   long long cyc_wait;        // SM cycles spent waiting for streamed log-prob rows (host input)
   uint32_t epoch;          // stamps the table entries of the current pass; survives InitDecoding
-  uint32_t pad0;
+  uint32_t st_redo;        // frames searched a second time because their table region filled up
   long long st_cand;     // emitting arcs that passed the running-cutoff filter
   long long st_items;    // arcs actually evaluated (scanned + looked up)
   // best-path selection results
@@ -237,6 +237,9 @@ struct Params {
   uint4 *front;     // kFrontCap per lane: {cost, state, number} of the tokens close to the best
   uint32_t hcap, hmask, lcap, qcap, ccap;
   int32_t hshift;
+  // a frame's region of the table: region_f entries per candidate, at least region_min
+  // (a power of two); region_f = 0: always the whole table
+  uint32_t region_f, region_min;
   int32_t cols;
   int32_t row_in_smem;
   // host-memory advance: rows [0, *progress) of every lane's staged matrix have
@@ -451,6 +454,11 @@ struct Shared {
   uint32_t hist[256];
   uint32_t warp_sums[32];
   uint32_t ex_coarse[33];  // t_ex[32 * q]: the top level of the item -> token search, bank by bank
+  // This frame's region of the lane's table: a power-of-two prefix sized from the frame's
+  // candidates (the table is empty between frames, so every frame may choose anew).
+  uint32_t hmask;
+  int32_t hshift;
+  uint32_t region_fail;    // the region filled up: the frame is searched again with the whole table
   long long t_mark;
   uint32_t cut_fkey;  // running next-frame cutoff, rounded UP to float (a filter only)
   uint32_t acc_emit, acc_eps, acc_expanded;  // per-frame counters
@@ -578,10 +586,17 @@ __device__ __forceinline__ LaneBuf lane_buffers(const Params &P, int lane) {
   return b;
 }
 
-__device__ __forceinline__ uint32_t table_hash(const Params &P, int32_t state) {
+__device__ __forceinline__ uint32_t table_hash(const Shared &sh, int32_t state) {
   // groups of 4 consecutive states share a 128-byte line; groups are scattered
-  return ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> P.hshift) << 2) |
+  return ((((static_cast<uint32_t>(state) >> 2) * 0x9E3779B1u) >> sh.hshift) << 2) |
          (static_cast<uint32_t>(state) & 3u);
+}
+
+// The whole table for the frame to come (the default; lane_expand_emitting may shrink it).
+__device__ __forceinline__ void table_region_reset(const Params &P, Shared &sh) {
+  sh.hmask = P.hmask;
+  sh.hshift = P.hshift;
+  sh.region_fail = 0;
 }
 
 // A slot that was just claimed joins this frame's slot list (its position there is the
@@ -591,12 +606,16 @@ __device__ __forceinline__ uint32_t register_claim(const Params &P, const LaneBu
                                                    uint32_t h, int32_t state, uint2 *eps_queue,
                                                    uint32_t *eps_queue_n) {
   const uint32_t pos = atomicAdd(&sh.list_n, 1u);
+  // (a region holds at most lcap entries unless it is the whole table: every claim made in a
+  // region is in the list, which is what the roll-back of a failed region walks)
   if (pos < P.lcap) {
     if (pos < static_cast<uint32_t>(kListSmem)) {
       B.s_list[pos] = h;
     } else {
       B.list[pos] = h;
     }
+    // half full: the whole table is the hard limit it always was, a region just gives up
+    if (pos > (sh.hmask >> 1) && sh.hmask != P.hmask) sh.region_fail = 1;
   } else {
     atomicOr(&sh.status, kStatusHashOverflow);
   }
@@ -631,7 +650,7 @@ __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf 
                                                  uint2 *eps_queue, uint32_t *eps_queue_n,
                                                  bool may_wait, bool *owner, HVal *cur,
                                                  uint32_t h_start = kNoIdx) {
-  uint32_t h = h_start == kNoIdx ? table_hash(P, state) : h_start;
+  uint32_t h = h_start == kNoIdx ? table_hash(sh, state) : h_start;
   // Frames in which most arrivals meet a state that is already there (H-like graphs: every
   // state is reached through hundreds of arcs) look at the entry first: a valid entry of
   // this state saves the atomic.  The bitmap stays the authority for everything else.
@@ -643,7 +662,9 @@ __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf 
       return h;
     }
   }
-  for (uint32_t probe = 0; probe < P.hcap; ++probe) {
+  for (uint32_t probe = 0; probe <= sh.hmask; ++probe) {
+    // (a region that has given up is not probed to the bitter end: the frame is redone)
+    if (probe >= 64u && *reinterpret_cast<volatile uint32_t *>(&sh.region_fail) != 0) return kNoIdx;
     const uint32_t bit = 1u << (h & 31u);
     const uint32_t old = atomicOr(B.bitmap + (h >> 5), bit);
     if ((old & bit) == 0) {
@@ -670,9 +691,13 @@ __device__ __forceinline__ uint32_t table_arrive(const Params &P, const LaneBuf 
       *cur = w.val;
       return h;
     }
-    h = (h + 1) & P.hmask;
+    h = (h + 1) & sh.hmask;
   }
-  atomicOr(&sh.status, kStatusHashOverflow);
+  if (sh.hmask != P.hmask) {
+    sh.region_fail = 1;
+  } else {
+    atomicOr(&sh.status, kStatusHashOverflow);
+  }
   return kNoIdx;
 }
 
@@ -1014,8 +1039,11 @@ __device__ __noinline__ uint32_t lane_compact_arena(const LaneBuf &B, Shared &sh
 // good_cut is handed to the next frame's scan, which takes the tokens below it
 // first: its running cutoff tightens early and few arcs that the exact cutoff
 // rejects become candidates.
+// Returns true if the frame has to be searched again: its table region filled up (the
+// closure can multiply the tokens of a frame many times over at word boundaries, which the
+// candidate count does not show); the table is back to empty then and nothing was committed.
 template <int THREADS, bool SIMPLE>
-__device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
+__device__ bool lane_closure_and_commit(const Params &P, const LaneBuf &B, Shared &sh,
                                         LaneState &ls, double cstar, double good_cut,
                                         double mid_cut) {
   const int tid = threadIdx.x;
@@ -1040,7 +1068,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
   long long sweeps = 0;
   while (true) {
     const uint32_t qn = min(sh.q_n[cur], P.qcap);
-    if (qn == 0 || sh.status != 0) break;
+    if (qn == 0 || sh.status != 0 || sh.region_fail != 0) break;
     __syncthreads();
     if (tid == 0) sh.q_n[cur ^ 1] = 0;
     __syncthreads();
@@ -1052,6 +1080,26 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     ++sweeps;
   }
   __syncthreads();
+  if (sh.region_fail != 0) {
+    // Roll the frame back: release every entry claimed (all of them are in the slot list), let
+    // their contents go stale (new epoch), forget the worklists.
+    const uint32_t claimed = min(sh.list_n, P.lcap);
+    for (uint32_t p = tid; p < claimed; p += THREADS) {
+      const uint32_t h = p < static_cast<uint32_t>(kListSmem) ? B.s_list[p] : B.list[p];
+      B.bitmap[h >> 5] = 0u;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      ls.epoch = ls.epoch + 1u == 0xFFFFFFFFu ? 0u : ls.epoch + 1u;
+      ls.st_redo += 1u;
+      ls.cyc_closure += clock64() - t_begin;
+      sh.list_n = 0;
+      sh.q_n[0] = 0;
+      sh.q_n[1] = 0;
+    }
+    __syncthreads();
+    return true;
+  }
   const long long t_mid = clock64();
   // ---- commit: one pass over the slot list.  Tokens are numbered in claim order
   // (Entry::idx, written when the slot was claimed), so the predecessor number that
@@ -1189,6 +1237,7 @@ __device__ void lane_closure_and_commit(const Params &P, const LaneBuf &B, Share
     sh.q_n[0] = 0;
   }
   __syncthreads();
+  return false;
 }
 
 // Recombines one emitting arc that survived pruning at its destination state: the entry
@@ -1249,7 +1298,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
                                        const float *next_row_g, float *s_row,
                                        double *t_cost, uint32_t *t_ex, uint32_t *t_beg,
                                        int32_t *t_tab, uint32_t *t_tok, uint16_t *lab_order,
-                                       uint16_t *bin_start) {
+                                       uint16_t *bin_start, bool whole_table) {
   constexpr int KT = kTileTokens;
   constexpr int TT = THREADS * KT;
   constexpr int NW = THREADS / 32;
@@ -1298,6 +1347,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     sh.acc_emit = sh.acc_expanded = sh.acc_items = 0;
     sh.cand_n = 0;
     sh.park_n = 0;
+    table_region_reset(P, sh);  // (arcs recombined during the scan -- candidate buffer full -- see the whole table)
   }
   double wc;
   float abf;
@@ -1672,6 +1722,24 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
   // ---------------------------------------------------------------- recombine
   const uint32_t n_cand = min(sh.cand_n, P.ccap);
   if (tid == 0) ls.st_cand += sh.cand_n;
+  // The frame's region of the table: P.region_f entries per candidate.  An entry access is a
+  // random 32-byte sector of 8 MB per lane; hashing a frame of ~1000 candidates into the first
+  // 16 k entries instead keeps the bitmap words and most of the entries of the lanes in flight
+  // in L2 (profiles/r2_sweeps.txt, section 14).  The candidates bound the emitting arrivals, not
+  // what the epsilon closure adds: a region that fills up makes the frame start over with the
+  // whole table (lane_closure_and_commit).
+  if (P.region_f > 0 && !whole_table && sh.cand_n <= P.ccap) {
+    __syncthreads();  // (the table is still empty: nothing was recombined during the scan)
+    if (tid == 0) {
+      uint32_t r = P.region_min;
+      while (r < P.region_f * n_cand && r < P.hcap) r <<= 1;
+      if (r < P.hcap) {
+        sh.hmask = r - 1u;
+        sh.hshift = 34 - (31 - __clz(r));
+      }
+    }
+    __syncthreads();
+  }
   // (Measured and rejected: taking 2-4 candidates per thread through the dependent
   // loads together -- the recombination gets faster, the other phases of the co-resident
   // lanes slower by as much; claiming the slot with the CAS before any probe load.)
@@ -1706,7 +1774,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
     }
     const int2 no = gld(P.e_no + c.z);
     const int32_t state = no.x & 0x7FFFFFFF;
-    const uint32_t h = table_hash(P, state);
+    const uint32_t h = table_hash(sh, state);
     const uint32_t bit = 1u << (h & 31u);
     const uint32_t old = atomicOr(B.bitmap + (h >> 5), bit);
     if ((old & bit) == 0) {
@@ -1746,7 +1814,7 @@ __device__ double lane_expand_emitting(const Params &P, const LaneBuf &B, Shared
         h = table_arrive(P, B, sh, ls.epoch, state, mine,
                          static_cast<int32_t>(r.y) < 0 ? B.queue : nullptr, &sh.q_n[0], true,
                          &owner, &cur,
-                         w.key != state && w.epoch == ls.epoch ? ((r.x + 1) & P.hmask) : r.x);
+                         w.key != state && w.epoch == ls.epoch ? ((r.x + 1) & sh.hmask) : r.x);
         if (h == kNoIdx || owner) continue;
       }
       while (mine.cost < cur.cost || (mine.cost == cur.cost && mine.arg < cur.arg)) {
@@ -2088,8 +2156,10 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
       sh.yield = 0;
       sh.load_first = 0;
       sh.cand_n = 0;
+      table_region_reset(P, sh);
     }
     __syncthreads();
+    bool whole_table = false;  // the frame is a second attempt (its table region filled up)
     while (true) {
       double cstar, good_cut, mid_cut;
       int n_in = 0, frame = 0;
@@ -2139,12 +2209,28 @@ __global__ void __launch_bounds__(THREADS) __maxnreg__(advance_max_regs(THREADS,
         uint16_t *lab_order = reinterpret_cast<uint16_t *>(s_row + (ROW_SMEM ? P.cols : 0));
         cstar = lane_expand_emitting<THREADS, ROW_SMEM, SIMPLE>(P, B, sh, ls, row_g, next_row_g,
                                                                 s_row, t_cost, t_ex, t_beg, t_tab,
-                                                                t_tok, lab_order, bin_start);
+                                                                t_tok, lab_order, bin_start, whole_table);
         // min(new_weight) = cstar - adaptive_beam is not kept; cstar - beam is at least as large
         good_cut = cstar - 0.75 * static_cast<double>(P.beam);
         mid_cut = cstar - 0.25 * static_cast<double>(P.beam);
       }
-      lane_closure_and_commit<THREADS, SIMPLE>(P, B, sh, ls, cstar, good_cut, mid_cut);
+      if (lane_closure_and_commit<THREADS, SIMPLE>(P, B, sh, ls, cstar, good_cut, mid_cut)) {
+        // The frame's table region filled up: the same frame once more, with the whole table.
+        // The next frame's row may be on its way into the row buffer: it is waited for, and
+        // this frame's row is loaded again.
+        if (sh.row_pending != 0) {
+          mbar_wait(&sh.row_bar, sh.row_parity);
+          __syncthreads();
+          if (tid == 0) {
+            sh.row_parity ^= 1u;
+            sh.row_pending = 0;
+          }
+          __syncthreads();
+        }
+        whole_table = true;
+        continue;
+      }
+      whole_table = false;
       if (tid == 0) {
         if (init_pass) {
           ls.st_sweeps = 0;
@@ -2197,6 +2283,7 @@ __global__ void __launch_bounds__(THREADS) kd_init_kernel(Params P) {
     sh.q_n[0] = 0;
     sh.load_first = 0;
     sh.cand_n = 0;
+    table_region_reset(P, sh);
   }
   __syncthreads();
   if (tid == 0) lane_start_token(P, B, sh, ls.epoch);

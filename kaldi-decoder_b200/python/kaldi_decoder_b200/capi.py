@@ -44,7 +44,7 @@ class KdStats(C.Structure):
                                          "cycles_cutoff", "cycles_expand", "cycles_closure",
                                          "cycles_commit", "slots_claimed", "candidates",
                                          "arcs_evaluated", "cycles_scan", "arena_compactions",
-                                         "cycles_input_wait")]
+                                         "cycles_input_wait", "table_retries")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -124,6 +124,50 @@ def test_fused_decode_is_one_launch_and_equals_the_stepwise_calls():
             assert _same_raw(again[u], pb[u])
 
 
+@pytest.mark.parametrize("region", ["1,64", "2,256", "0"])
+def test_a_frame_whose_table_region_fills_up_is_searched_again(region, monkeypatch):
+    """A frame hashes into a region of its lane's table sized from its candidate count; the
+    epsilon closure can outgrow it, then the frame is rolled back and searched again with the
+    whole table.  Tiny regions (KD_B200_TABLE_REGION) make that the common case: tokens after
+    every frame, best paths and ReachedFinal must still be the oracle's, fused and streaming."""
+    monkeypatch.setenv("KD_B200_TABLE_REGION", region)
+    g = small_graph("HLG")
+    n, T = 8, 90
+    mats = [synth.make_logprobs(g, T - 5 * u, seed=500 + u, peak=7) for u in range(n)]
+    want = _oracle_paths(g, mats, OPTS)
+    dg = capi.DeviceGraph.from_graph(g)
+    dec = capi.LaneDecoder(dg, capi.make_options(**OPTS), max_lanes=n, hash_capacity=1 << 14,
+                           arena_records=1 << 19)
+    lanes = list(range(n))
+    pb = dec.decode(lanes, mats, True)
+    retries = dec.stats()["table_retries"]
+    if region == "1,64":
+        assert retries > 0
+    if region == "0":
+        assert retries == 0
+    for u in lanes:
+        ob, (os_, oc), rf = want[u]
+        assert _same_raw(pb[u], ob), u
+        assert pb[u].reached_final == rf
+        gs, gc = sorted_tokens(*dec.tokens(u))
+        assert np.array_equal(gs, os_) and np.array_equal(gc, oc)
+    # frame by frame from host memory (the row of a frame that starts over is loaded again;
+    # the prefetched next row must not be lost), tokens checked after every frame
+    og = kd_oracle.OracleGraph(g)
+    o = kd_oracle.OracleDecoder(og, kd_ref.Options(**OPTS), kd_oracle.CANONICAL)
+    o.init_decoding()
+    dec.init([0])
+    m = mats[0]
+    for f in range(0, m.shape[0], 3):
+        k = min(3, m.shape[0] - f)
+        o.advance_decoding(m, 0, k)
+        dec.advance([0], [m], max_num_frames=k)
+        gs, gc = sorted_tokens(*dec.tokens(0))
+        os_, oc = sorted_tokens(*o.tokens())
+        assert np.array_equal(gs, os_) and np.array_equal(gc, oc), f
+    assert _same_raw(dec.best_paths([0], True)[0], o.get_best_path(True, raw=True))
+
+
 def test_two_lane_groups_in_flight_and_deferred_sync():
     """Two calls in flight on disjoint lanes; touching a lane completes the call that owns it."""
     g = small_graph("HL")

@@ -45,6 +45,8 @@ for cfg in (sys.argv[1:] or ["C1", "C2", "C3", "C4"]):
                        "--steps 1 --warmup 1" % (cfg, FRAMES)}
     print(cfg, rec[cfg])
     json.dump(rec, open(out_path, "w"), indent=1)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "r2_dram_bytes.json"), "w"), indent=1)
 # (the file is written under profiles/ of the box's copy: also leave it where gpurun merges it back)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "r2_dram_bytes.json"), "w"), indent=1)
