@@ -24,6 +24,21 @@ def test_capi_library_exports_every_declared_symbol():
         assert getattr(lib, name) is not None
 
 
+def test_ctypes_structs_mirror_the_header():
+    """capi.py restates kd_options / kd_decoder_config / kd_stats for ctypes: same fields, same
+    order, same widths as include/kd_capi.h (a field added on one side only would shift every
+    counter after it)."""
+    header = open(os.path.join(ROOT, "include", "kd_capi.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    ctype = {"int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "float": ctypes.c_float}
+    for cname, pystruct in (("kd_options", capi.KdOptions), ("kd_decoder_config", capi.KdConfig),
+                            ("kd_stats", capi.KdStats)):
+        body = re.search(r"typedef struct\s*\w*\s*\{([^}]*)\}\s*%s\s*;" % cname, header).group(1)
+        fields = re.findall(r"(int32_t|int64_t|float)\s+(\w+)\s*;", body)
+        assert [(n, ctype[t]) for t, n in fields] == list(pystruct._fields_), cname
+    assert "table_retries" in dict(capi.KdStats._fields_)
+
+
 def test_capi_fails_loudly_without_a_gpu():
     if capi.device_count() > 0:
         pytest.skip("a GPU is present")
